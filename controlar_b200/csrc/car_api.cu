@@ -1,0 +1,563 @@
+// car_api.cu — C-ABI entry points (include/controlar_b200.h) and the host-side chaining of the AR kernels.
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+
+#include "common.cuh"
+#include "gemm_skinny.cuh"
+#include "attention.cuh"
+#include "sampler.cuh"
+#include "misc.cuh"
+
+thread_local std::string g_car_err;
+std::atomic<long long> g_car_launches{0};
+
+// ---------------------------------------------------------------------------------------------------------
+// structures
+// ---------------------------------------------------------------------------------------------------------
+struct CarModel {
+    CarModelDesc d;
+    // borrowed originals
+    const void *tok_emb, *norm, *output, *cap_fc1, *cap_fc2, *label_table, *cond_fc1, *cond_fc2, *ctl_fc1[3], *ctl_fc2[3];
+    std::vector<const void*> attention_norm, wqkv, wo, ffn_norm, w1, w3, w2;
+    // owned GEMM-ready copies: bf16 -> fragment-packed; fp32 -> plain (only w13 is an owned interleaved copy)
+    std::vector<void*> g_wqkv, g_wo, g_w13, g_w2;
+    void *g_output, *g_cap_fc1, *g_cap_fc2, *g_cond_fc1, *g_cond_fc2, *g_ctl_fc1[3], *g_ctl_fc2[3];
+    std::vector<void*> owned;
+    size_t esize() const { return d.dtype == CAR_BF16 ? 2 : 4; }
+};
+
+struct CarState {
+    CarModel* m;
+    int b_eff, S, N, T;
+    std::vector<void*> kc, vc;
+    const float* rope;
+    int* emb_mask;       // [b_eff][T] or null (= all ones)
+    int* emb_mask_store;
+    // decode scratch (b_eff rows)
+    void *h, *q, *attn, *act;
+    float* logits;       // [b_eff][V]
+    int *tok, *pos, *done_ctr, *tickets, *tokens;
+    float* attn_part;
+    int nsplit;
+    // control tokens [3][b_eff][N][d]
+    void* ctrl[3];
+    bool has_ctrl;
+    float cs;
+    // prefill scratch
+    void *hP, *qP, *attnP, *actP, *t1, *t2;
+    bool prefilled;
+    // decode graph
+    cudaGraphExec_t gexec;
+    bool graph_ok;
+    CarSampling gsp;
+    const float* gnoise;
+    std::vector<void*> owned;
+};
+
+static int alloc_dev(std::vector<void*>& owned, void** p, size_t bytes) {
+    CAR_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    owned.push_back(*p);
+    return CAR_OK;
+}
+
+extern "C" const char* car_last_error(void) { return g_car_err.c_str(); }
+extern "C" int car_version(void) { return 100; }
+extern "C" int64_t car_launch_count(int32_t reset) {
+    long long v = g_car_launches.load();
+    if (reset) g_car_launches.store(0);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// skinny GEMM dispatch
+// ---------------------------------------------------------------------------------------------------------
+template <int NB, int U, bool NORM>
+static int launch_skinny_bf16_inst(cudaStream_t st, const bf16* A, int lda, const void* Wp, const bf16* nw, float eps,
+                                   int M, int nblk, int K, const EpiParams& ep) {
+    static bool attr_set = false;
+    const size_t smem = skinny_smem_bytes(K, NB);
+    if (!attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(skinny_gemm_bf16<NB, U, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "K too large for the shared-memory activation tile");
+    dim3 grid((nblk + NB - 1) / NB, (M + 15) / 16);
+    CAR_LAUNCH((skinny_gemm_bf16<NB, U, NORM>), grid, SK_THREADS, smem, st, A, lda, (const uint4*)Wp, nw, eps, K, nblk, ep);
+    return CAR_OK;
+}
+
+template <int NB, bool NORM>
+static int launch_skinny_bf16_u(cudaStream_t st, int U, const bf16* A, int lda, const void* Wp, const bf16* nw, float eps,
+                                int M, int nblk, int K, const EpiParams& ep) {
+    switch (U) {
+        case 5: return launch_skinny_bf16_inst<NB, 5, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        case 7: return launch_skinny_bf16_inst<NB, 7, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        default: return launch_skinny_bf16_inst<NB, 4, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+    }
+}
+
+// W: bf16 -> packed (pack_weight_bf16_kernel) ; fp32 -> plain [N][K].  N = 8*nblk rows of W.
+static int launch_skinny(cudaStream_t st, int dtype, const void* A, int lda, const void* W, const void* nw, float eps,
+                         int M, int N, int K, EpiParams ep, bool norm) {
+    if (K % 64 != 0 || N % 8 != 0) CAR_FAIL(CAR_ERR_UNSUPPORTED, "skinny GEMM needs K % 64 == 0 and N % 8 == 0");
+    if (M <= 0) return CAR_OK;
+    ep.M = M;
+    const int nblk = N / 8;
+    if (dtype == CAR_F32) {
+        dim3 grid((nblk + 1) / 2, (M + 15) / 16);
+        if (norm) CAR_LAUNCH((skinny_gemm_f32<true>), grid, SK_THREADS, 0, st, (const float*)A, lda, (const float*)W, (const float*)nw, eps, K, nblk, ep);
+        else CAR_LAUNCH((skinny_gemm_f32<false>), grid, SK_THREADS, 0, st, (const float*)A, lda, (const float*)W, (const float*)nw, eps, K, nblk, ep);
+        return CAR_OK;
+    }
+    const int mtiles = (M + 15) / 16;
+    const int nsteps = ((K >> 5) + SK_WARPS - 1) / SK_WARPS;
+    int U = 4;
+    if (nsteps % 7 == 0) U = 7; else if (nsteps % 5 == 0) U = 5;
+    int NB;
+    if (mtiles > 1) NB = 4;                       // M-tiled (prefill): maximise reuse of the activation tile
+    else {
+        const int want = nblk / 148;              // aim at >= one CTA per SM
+        NB = want >= 4 ? 4 : (want >= 2 ? 2 : 1);
+        const bool big_tile = skinny_smem_bytes(K, 1) > 100 * 1024;   // one CTA per SM: avoid a 2nd partial wave
+        if (big_tile && nblk > 148 && NB == 1) NB = 2;
+    }
+    if (ep.kind == EPI_SWIGLU && NB == 1) NB = 2;
+    if (NB * U > 16) U = 4;                       // register budget
+    const bf16* Ab = (const bf16*)A; const bf16* nwb = (const bf16*)nw;
+#define CAR_SK(NB_) (norm ? launch_skinny_bf16_u<NB_, true>(st, U, Ab, lda, W, nwb, eps, M, nblk, K, ep) \
+                          : launch_skinny_bf16_u<NB_, false>(st, U, Ab, lda, W, nwb, eps, M, nblk, K, ep))
+    switch (NB) {
+        case 4: return CAR_SK(4);
+        case 2: return CAR_SK(2);
+        default: return CAR_SK(1);
+    }
+#undef CAR_SK
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------
+static int pack_one(CarModel* m, cudaStream_t st, const void* w, const void* w3, int N, int K, bool interleave, void** dst,
+                    bool allocate) {
+    // N = rows of the logical (possibly interleaved) matrix
+    if (m->d.dtype == CAR_BF16) {
+        if (allocate) CAR_TRY(alloc_dev(m->owned, dst, (size_t)N * K * 2));
+        const int nblk = N / 8;
+        const long long total = (long long)nblk * (K / 32) * 32;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+        CAR_LAUNCH(pack_weight_bf16_kernel, blocks, 256, 0, st, (const bf16*)w, (const bf16*)w3, (uint4*)*dst, nblk, K, interleave ? 1 : 0);
+    } else {
+        if (!interleave) { *dst = const_cast<void*>(w); return CAR_OK; }
+        if (allocate) CAR_TRY(alloc_dev(m->owned, dst, (size_t)N * K * 4));
+        CAR_LAUNCH(interleave_rows_f32_kernel, 2048, 256, 0, st, (const float*)w, (const float*)w3, (float*)*dst, N / 2, K);
+    }
+    return CAR_OK;
+}
+
+static int model_pack_all(CarModel* m, const CarWeights* w, cudaStream_t st, bool allocate) {
+    const CarModelDesc& d = m->d;
+    const int L = d.n_layer;
+    m->tok_emb = w->tok_embeddings; m->norm = w->norm; m->output = w->output;
+    m->cap_fc1 = w->cap_fc1; m->cap_fc2 = w->cap_fc2; m->label_table = w->label_table;
+    m->cond_fc1 = w->cond_fc1; m->cond_fc2 = w->cond_fc2;
+    for (int j = 0; j < 3; ++j) { m->ctl_fc1[j] = w->ctl_fc1[j]; m->ctl_fc2[j] = w->ctl_fc2[j]; }
+    m->attention_norm.assign(w->attention_norm, w->attention_norm + L);
+    m->wqkv.assign(w->wqkv, w->wqkv + L); m->wo.assign(w->wo, w->wo + L);
+    m->ffn_norm.assign(w->ffn_norm, w->ffn_norm + L);
+    m->w1.assign(w->w1, w->w1 + L); m->w3.assign(w->w3, w->w3 + L); m->w2.assign(w->w2, w->w2 + L);
+    if (allocate) { m->g_wqkv.assign(L, nullptr); m->g_wo.assign(L, nullptr); m->g_w13.assign(L, nullptr); m->g_w2.assign(L, nullptr); }
+    for (int l = 0; l < L; ++l) {
+        CAR_TRY(pack_one(m, st, m->wqkv[l], nullptr, 3 * d.dim, d.dim, false, &m->g_wqkv[l], allocate));
+        CAR_TRY(pack_one(m, st, m->wo[l], nullptr, d.dim, d.dim, false, &m->g_wo[l], allocate));
+        CAR_TRY(pack_one(m, st, m->w1[l], m->w3[l], 2 * d.ffn_dim, d.dim, true, &m->g_w13[l], allocate));
+        CAR_TRY(pack_one(m, st, m->w2[l], nullptr, d.dim, d.ffn_dim, false, &m->g_w2[l], allocate));
+    }
+    CAR_TRY(pack_one(m, st, m->output, nullptr, d.vocab_size, d.dim, false, &m->g_output, allocate));
+    if (d.model_type == 1) {
+        if (!m->cap_fc1 || !m->cap_fc2) CAR_FAIL(CAR_ERR_ARG, "t2i model needs cap_fc1/cap_fc2");
+        CAR_TRY(pack_one(m, st, m->cap_fc1, nullptr, d.dim, d.caption_dim, false, &m->g_cap_fc1, allocate));
+        CAR_TRY(pack_one(m, st, m->cap_fc2, nullptr, d.dim, d.dim, false, &m->g_cap_fc2, allocate));
+    } else if (!m->label_table) CAR_FAIL(CAR_ERR_ARG, "c2i model needs label_table");
+    CAR_TRY(pack_one(m, st, m->cond_fc1, nullptr, d.dim, d.dim, false, &m->g_cond_fc1, allocate));
+    CAR_TRY(pack_one(m, st, m->cond_fc2, nullptr, d.dim, d.dim, false, &m->g_cond_fc2, allocate));
+    for (int j = 0; j < 3; ++j) {
+        CAR_TRY(pack_one(m, st, m->ctl_fc1[j], nullptr, d.dim, d.dim, false, &m->g_ctl_fc1[j], allocate));
+        CAR_TRY(pack_one(m, st, m->ctl_fc2[j], nullptr, d.dim, d.dim, false, &m->g_ctl_fc2[j], allocate));
+    }
+    return CAR_OK;
+}
+
+extern "C" int car_model_create(const CarModelDesc* desc, const CarWeights* w, void* stream, CarModel** out) {
+    if (!desc || !w || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    const CarModelDesc& d = *desc;
+    if (d.dtype != CAR_BF16 && d.dtype != CAR_F32) CAR_FAIL(CAR_ERR_ARG, "dtype must be CAR_BF16 or CAR_F32");
+    if (d.n_head <= 0 || d.dim != d.n_head * 64) CAR_FAIL(CAR_ERR_UNSUPPORTED, "head_dim must be 64");
+    if (d.n_layer <= 0 || d.n_layer % 3 != 0) CAR_FAIL(CAR_ERR_UNSUPPORTED, "n_layer must be a multiple of 3 (gpt_t2i.py:320,457)");
+    if (d.dim % 64 || d.ffn_dim % 64 || d.vocab_size % 8) CAR_FAIL(CAR_ERR_UNSUPPORTED, "dim, ffn_dim must be multiples of 64; vocab of 8");
+    if (d.model_type == 1 && d.caption_dim % 64) CAR_FAIL(CAR_ERR_UNSUPPORTED, "caption_dim must be a multiple of 64");
+    if (d.cls_token_num < 1 || d.cls_token_num > 256) CAR_FAIL(CAR_ERR_UNSUPPORTED, "cls_token_num must be in [1,256]");
+    CarModel* m = new CarModel();
+    m->d = d;
+    int r = model_pack_all(m, w, (cudaStream_t)stream, true);
+    if (r != CAR_OK) { for (void* p : m->owned) cudaFree(p); delete m; return r; }
+    *out = m;
+    return CAR_OK;
+}
+
+extern "C" int car_model_repack(CarModel* m, const CarWeights* w, void* stream) {
+    if (!m || !w) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    return model_pack_all(m, w, (cudaStream_t)stream, false);
+}
+
+extern "C" int car_model_destroy(CarModel* m) {
+    if (!m) return CAR_OK;
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N, void* const* k_cache, void* const* v_cache,
+                                const float* rope_table, CarState** out) {
+    if (!m || !k_cache || !v_cache || !rope_table || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    const CarModelDesc& d = m->d;
+    const int T = d.cls_token_num;
+    if (b_eff <= 0 || N <= 0 || S < T + N) CAR_FAIL(CAR_ERR_ARG, "need b_eff > 0, N > 0, S >= T + N");
+    if (N > d.block_size) CAR_FAIL(CAR_ERR_ARG, "N exceeds block_size (RoPE table rows)");
+    CarState* s = new CarState();
+    s->m = m; s->b_eff = b_eff; s->S = S; s->N = N; s->T = T;
+    s->kc.assign(k_cache, k_cache + d.n_layer); s->vc.assign(v_cache, v_cache + d.n_layer);
+    s->rope = rope_table; s->emb_mask = nullptr; s->has_ctrl = false; s->cs = 1.f; s->prefilled = false;
+    s->gexec = nullptr; s->graph_ok = false; s->gnoise = nullptr;
+    const size_t es = m->esize();
+    const size_t dd = d.dim, F = d.ffn_dim, V = d.vocab_size;
+    const size_t MP = (size_t)b_eff * T, MC = (size_t)b_eff * N;
+    s->nsplit = std::max(1, std::min(16, (4 * 148 + b_eff * d.n_head - 1) / (b_eff * d.n_head)));
+    int r = CAR_OK;
+    auto A = [&](void** p, size_t bytes) { if (r == CAR_OK) r = alloc_dev(s->owned, p, bytes); };
+    A(&s->h, b_eff * dd * es); A(&s->q, b_eff * dd * es); A(&s->attn, b_eff * dd * es); A(&s->act, b_eff * F * es);
+    A((void**)&s->logits, b_eff * V * 4); A((void**)&s->tok, b_eff * 4); A((void**)&s->pos, 4 * 4);
+    A((void**)&s->tickets, (size_t)b_eff * d.n_head * 4);
+    A((void**)&s->tokens, (size_t)b_eff * N * 4);
+    A((void**)&s->attn_part, (size_t)b_eff * d.n_head * s->nsplit * AD_PART * 4);
+    for (int j = 0; j < 3; ++j) A(&s->ctrl[j], MC * dd * es);
+    A(&s->hP, MP * dd * es); A(&s->qP, MP * dd * es); A(&s->attnP, MP * dd * es); A(&s->actP, MP * F * es);
+    A(&s->t1, std::max(MC, MP) * dd * es); A(&s->t2, std::max(MC, MP) * dd * es);
+    A((void**)&s->emb_mask, MP * 4);
+    if (r == CAR_OK && cudaMemset(s->tickets, 0, (size_t)b_eff * d.n_head * 4) != cudaSuccess) r = CAR_ERR_CUDA;
+    if (r == CAR_OK && cudaMemset(s->pos, 0, 16) != cudaSuccess) r = CAR_ERR_CUDA;
+    if (r != CAR_OK) { for (void* p : s->owned) cudaFree(p); delete s; return r; }
+    s->done_ctr = s->pos + 1;
+    s->emb_mask_store = s->emb_mask;
+    s->emb_mask = nullptr;                           // all-ones until car_state_set_emb_mask
+    s->gsp = CarSampling{};
+    *out = s;
+    return CAR_OK;
+}
+
+extern "C" int car_state_set_emb_mask(CarState* s, const int32_t* emb_mask_dev, void* stream) {
+    if (!s) CAR_FAIL(CAR_ERR_ARG, "null state");
+    if (!emb_mask_dev) { s->emb_mask = nullptr; return CAR_OK; }
+    CAR_CUDA(cudaMemcpyAsync(s->emb_mask_store, emb_mask_dev, (size_t)s->b_eff * s->T * 4, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    s->emb_mask = s->emb_mask_store;
+    return CAR_OK;
+}
+
+extern "C" int car_state_destroy(CarState* s) {
+    if (!s) return CAR_OK;
+    if (s->gexec) cudaGraphExecDestroy(s->gexec);
+    for (void* p : s->owned) if (p) cudaFree(p);
+    delete s;
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel chains
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_attn_decode(CarState* s, int l, cudaStream_t st) {
+    const CarModelDesc& d = s->m->d;
+    dim3 grid(s->b_eff * d.n_head, s->nsplit);
+    CAR_LAUNCH((attn_decode_kernel<T>), grid, AD_THREADS, 0, st, (const T*)s->q, (const T*)s->kc[l], (const T*)s->vc[l],
+               (const int*)s->emb_mask, s->T, (const int*)s->pos, d.n_head, s->S, s->T, s->nsplit, s->attn_part, s->tickets,
+               (T*)s->attn);
+    return CAR_OK;
+}
+
+template <typename T>
+static int launch_attn_prefill(CarState* s, int l, cudaStream_t st) {
+    const CarModelDesc& d = s->m->d;
+    const long long items = (long long)s->b_eff * d.n_head * s->T;
+    CAR_LAUNCH((attn_prefill_kernel<T>), (unsigned)((items + 3) / 4), 128, 0, st, (const T*)s->qP, (const T*)s->kc[l],
+               (const T*)s->vc[l], (const int*)s->emb_mask, s->T, s->b_eff, d.n_head, s->S, s->T, s->T, (T*)s->attnP);
+    return CAR_OK;
+}
+
+static EpiParams epi_base(int kind) {
+    EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.kind = kind;
+    ep.rpb = 1;
+    return ep;
+}
+
+// one transformer block on `rows` rows; decode (rpb = 1, pos from device scalar) or prefill (rpb = T, pos = t)
+static int enqueue_block(CarState* s, int l, bool decode, cudaStream_t st) {
+    CarModel* m = s->m;
+    const CarModelDesc& d = m->d;
+    const int dt = d.dtype, dim = d.dim, F = d.ffn_dim;
+    const int rows = decode ? s->b_eff : s->b_eff * s->T;
+    void* h = decode ? s->h : s->hP;
+    void* q = decode ? s->q : s->qP;
+    void* attn = decode ? s->attn : s->attnP;
+    void* act = decode ? s->act : s->actP;
+    const int rpb = decode ? 1 : s->T;
+    const int* posp = decode ? s->pos : nullptr;
+
+    EpiParams e1 = epi_base(EPI_QKV);
+    e1.rpb = rpb; e1.pos_ptr = posp; e1.rope = s->rope; e1.kc = s->kc[l]; e1.vc = s->vc[l]; e1.q = q; e1.S = s->S;
+    e1.H = d.n_head; e1.d = dim;
+    CAR_TRY(launch_skinny(st, dt, h, dim, m->g_wqkv[l], m->attention_norm[l], d.norm_eps, rows, 3 * dim, dim, e1, true));
+
+    if (decode) { if (dt == CAR_BF16) CAR_TRY(launch_attn_decode<bf16>(s, l, st)); else CAR_TRY(launch_attn_decode<float>(s, l, st)); }
+    else { if (dt == CAR_BF16) CAR_TRY(launch_attn_prefill<bf16>(s, l, st)); else CAR_TRY(launch_attn_prefill<float>(s, l, st)); }
+
+    EpiParams e2 = epi_base(EPI_RESID);
+    e2.rpb = rpb; e2.pos_ptr = posp; e2.h = h; e2.ldh = dim;
+    CAR_TRY(launch_skinny(st, dt, attn, dim, m->g_wo[l], nullptr, 0.f, rows, dim, dim, e2, false));
+
+    EpiParams e3 = epi_base(EPI_SWIGLU);
+    e3.rpb = rpb; e3.out = act; e3.ldo = F;
+    CAR_TRY(launch_skinny(st, dt, h, dim, m->g_w13[l], m->ffn_norm[l], d.norm_eps, rows, 2 * F, dim, e3, true));
+
+    EpiParams e4 = epi_base(EPI_RESID);
+    e4.rpb = rpb; e4.pos_ptr = posp; e4.h = h; e4.ldh = dim;
+    const int step3 = d.n_layer / 3;
+    if (decode && s->has_ctrl && (l + 1) < d.n_layer && (l + 1) % step3 == 0) {
+        // control add of the NEXT layer group fused here (gpt_t2i.py:466)
+        e4.ctrl = s->ctrl[(l + 1) / step3]; e4.n_img = s->N; e4.T = s->T; e4.cs = s->cs;
+    }
+    CAR_TRY(launch_skinny(st, dt, act, F, m->g_w2[l], nullptr, 0.f, rows, dim, F, e4, false));
+    return CAR_OK;
+}
+
+static int enqueue_head(CarState* s, const void* hrows, int rows, float* logits, cudaStream_t st) {
+    CarModel* m = s->m;
+    const CarModelDesc& d = m->d;
+    EpiParams e = epi_base(EPI_LOGITS);
+    e.logits = logits; e.ldl = d.vocab_size;
+    return launch_skinny(st, d.dtype, hrows, d.dim, m->g_output, m->norm, d.norm_eps, rows, d.vocab_size, d.dim, e, true);
+}
+
+static int enqueue_decode_layers(CarState* s, float* logits, cudaStream_t st) {
+    for (int l = 0; l < s->m->d.n_layer; ++l) CAR_TRY(enqueue_block(s, l, true, st));
+    return enqueue_head(s, s->h, s->b_eff, logits, st);
+}
+
+static int enqueue_mlp(CarState* s, const void* x, int rows, int K, const void* fc1, const void* fc2, void* tmp, void* out,
+                       cudaStream_t st) {
+    const CarModelDesc& d = s->m->d;
+    EpiParams a = epi_base(EPI_STORE);
+    a.out = tmp; a.ldo = d.dim; a.act = 1;
+    CAR_TRY(launch_skinny(st, d.dtype, x, K, fc1, nullptr, 0.f, rows, d.dim, K, a, false));
+    EpiParams b = epi_base(EPI_STORE);
+    b.out = out; b.ldo = d.dim; b.act = 0;
+    return launch_skinny(st, d.dtype, tmp, d.dim, fc2, nullptr, 0.f, rows, d.dim, d.dim, b, false);
+}
+
+template <typename T>
+static int prefill_small_kernels(CarState* s, int l, cudaStream_t st) {
+    const CarModelDesc& d = s->m->d;
+    const int step3 = d.n_layer / 3;
+    if (s->has_ctrl && l % step3 == 0)
+        CAR_LAUNCH((prefill_ctrl_add_kernel<T>), s->b_eff, 256, 0, st, (T*)s->hP, (const T*)s->ctrl[l / step3], s->T, s->N, d.dim, s->cs);
+    return CAR_OK;
+}
+
+extern "C" int car_prefill(CarState* s, const void* cond, const void* condition, float control_strength, float* logits_out,
+                           int32_t all_rows, void* stream) {
+    if (!s || !cond) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CarModel* m = s->m;
+    const CarModelDesc& d = m->d;
+    const int rows = s->b_eff * s->T;
+    s->cs = control_strength;
+    s->has_ctrl = condition != nullptr;
+    s->graph_ok = false;
+    // 1. prefix embeddings: CaptionEmbedder MLP (gpt_t2i.py:156-162) or LabelEmbedder gather (:89-97)
+    if (d.model_type == 1) CAR_TRY(enqueue_mlp(s, cond, rows, d.caption_dim, m->g_cap_fc1, m->g_cap_fc2, s->t1, s->hP, st));
+    else {
+        if (d.dtype == CAR_BF16) CAR_LAUNCH((gather_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)m->label_table, (const int*)cond, (bf16*)s->hP, d.dim, (const bf16*)nullptr, 0, 0, 0.f);
+        else CAR_LAUNCH((gather_rows_kernel<float>), rows, 256, 0, st, (const float*)m->label_table, (const int*)cond, (float*)s->hP, d.dim, (const float*)nullptr, 0, 0, 0.f);
+    }
+    // 2. control tokens: condition_mlp then the three condition_layers MLPs (gpt_t2i.py:438-442)
+    if (condition) {
+        const int crow = s->b_eff * s->N;
+        CAR_TRY(enqueue_mlp(s, condition, crow, d.dim, m->g_cond_fc1, m->g_cond_fc2, s->t1, s->t2, st));
+        for (int j = 0; j < 3; ++j) CAR_TRY(enqueue_mlp(s, s->t2, crow, d.dim, m->g_ctl_fc1[j], m->g_ctl_fc2[j], s->t1, s->ctrl[j], st));
+    }
+    // 3. blocks
+    for (int l = 0; l < d.n_layer; ++l) {
+        if (d.dtype == CAR_BF16) CAR_TRY(prefill_small_kernels<bf16>(s, l, st)); else CAR_TRY(prefill_small_kernels<float>(s, l, st));
+        CAR_TRY(enqueue_block(s, l, false, st));
+    }
+    // 4. head: last prefix row always (feeds car_generate); all rows on request (forward() parity)
+    if (d.dtype == CAR_BF16) CAR_LAUNCH((take_last_row_kernel<bf16>), s->b_eff, 256, 0, st, (const bf16*)s->hP, (bf16*)s->h, s->T, d.dim);
+    else CAR_LAUNCH((take_last_row_kernel<float>), s->b_eff, 256, 0, st, (const float*)s->hP, (float*)s->h, s->T, d.dim);
+    CAR_TRY(enqueue_head(s, s->h, s->b_eff, s->logits, st));
+    if (logits_out) {
+        if (all_rows) CAR_TRY(enqueue_head(s, s->hP, rows, logits_out, st));
+        else CAR_CUDA(cudaMemcpyAsync(logits_out, s->logits, (size_t)s->b_eff * d.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1);
+    s->prefilled = true;
+    return CAR_OK;
+}
+
+extern "C" int car_decode_step(CarState* s, const int32_t* tok, int32_t pos, float* logits_out, void* stream) {
+    if (!s || !tok || !logits_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (pos < s->T || pos >= s->S) CAR_FAIL(CAR_ERR_ARG, "pos out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CarModelDesc& d = s->m->d;
+    CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, pos);
+    const int p = pos - s->T + 1;
+    if (d.dtype == CAR_BF16)
+        CAR_LAUNCH((gather_rows_kernel<bf16>), s->b_eff, 256, 0, st, (const bf16*)s->m->tok_emb, (const int*)tok, (bf16*)s->h, d.dim,
+                   (const bf16*)(s->has_ctrl ? s->ctrl[0] : nullptr), s->N, p, s->cs);
+    else
+        CAR_LAUNCH((gather_rows_kernel<float>), s->b_eff, 256, 0, st, (const float*)s->m->tok_emb, (const int*)tok, (float*)s->h, d.dim,
+                   (const float*)(s->has_ctrl ? s->ctrl[0] : nullptr), s->N, p, s->cs);
+    return enqueue_decode_layers(s, logits_out, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sampling
+// ---------------------------------------------------------------------------------------------------------
+static int fill_sample_args(SampleArgs& a, const CarSampling* sp, int b_eff, int V) {
+    memset(&a, 0, sizeof(a));
+    a.V = V;
+    a.use_cfg = sp->cfg_scale > 1.0f ? 1 : 0;
+    if (a.use_cfg && (b_eff % 2)) CAR_FAIL(CAR_ERR_ARG, "cfg_scale > 1 needs an even number of rows");
+    a.B = a.use_cfg ? b_eff / 2 : b_eff;
+    a.cfg_on = 1; a.cfg_scale = sp->cfg_scale; a.cfg_interval = sp->cfg_interval;
+    a.inv_temp = 1.0f / fmaxf(sp->temperature, 1e-5f);
+    a.top_k = sp->top_k; a.top_p = sp->top_p; a.sample_logits = sp->sample_logits;
+    a.seed_lo = (uint32_t)(sp->seed & 0xffffffffu); a.seed_hi = (uint32_t)(sp->seed >> 32);
+    return CAR_OK;
+}
+
+static int launch_sampler(const SampleArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const size_t smem = (size_t)a.V * 4;
+    if (smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "vocab too large for the sampler's shared-memory row");
+    CAR_LAUNCH(sample_kernel, a.B, SMP_THREADS, smem, st, a);
+    return CAR_OK;
+}
+
+extern "C" int car_sample(const float* logits, int32_t b_eff, int32_t V, const CarSampling* sp, int32_t cfg_on, int32_t step,
+                          const float* noise, int32_t* idx_out, float* probs_out, void* stream) {
+    if (!logits || !sp || !idx_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    SampleArgs a;
+    CAR_TRY(fill_sample_args(a, sp, b_eff, V));
+    a.logits = logits; a.cfg_on = cfg_on; a.cfg_interval = -1; a.step = step; a.noise = noise;
+    a.idx_out = idx_out; a.tokens_ld = 0; a.probs_out = probs_out;
+    return launch_sampler(a, (cudaStream_t)stream);
+}
+
+static bool same_sampling(const CarSampling& x, const CarSampling& y) {
+    return x.temperature == y.temperature && x.top_k == y.top_k && x.top_p == y.top_p && x.sample_logits == y.sample_logits &&
+           x.cfg_scale == y.cfg_scale && x.cfg_interval == y.cfg_interval && x.seed == y.seed;
+}
+
+static int loop_sample_args(CarState* s, const CarSampling* sp, const float* noise, SampleArgs& a) {
+    const CarModelDesc& d = s->m->d;
+    CAR_TRY(fill_sample_args(a, sp, s->b_eff, d.vocab_size));
+    a.logits = s->logits; a.noise = noise; a.noise_per_step = noise ? 1 : 0;
+    a.idx_out = s->tokens; a.tokens_ld = s->N; a.probs_out = nullptr;
+    a.h_out = s->h; a.tok_emb = s->m->tok_emb; a.ctrl0 = s->has_ctrl ? s->ctrl[0] : nullptr; a.d = d.dim; a.n_img = s->N;
+    a.T = s->T; a.cs = s->cs; a.dtype = d.dtype; a.tok_buf = s->tok; a.pos_ptr = s->pos; a.done_ctr = s->done_ctr;
+    return CAR_OK;
+}
+
+extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise, int32_t* tokens_out,
+                            void* stream) {
+    if (!s || !sp || !tokens_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (!s->prefilled) CAR_FAIL(CAR_ERR_STATE, "car_generate must follow car_prefill on the same state");
+    if (n_tokens < 1 || n_tokens > s->N) CAR_FAIL(CAR_ERR_ARG, "n_tokens must be in [1, N]");
+    cudaStream_t st = (cudaStream_t)stream;
+    SampleArgs a;
+    CAR_TRY(loop_sample_args(s, sp, noise, a));
+    // token 0 from the prefill logits (generate.py:198); its fused tail writes h for position T and bumps pos
+    CAR_TRY(launch_sampler(a, st));
+    if (n_tokens > 1) {
+        if (!s->graph_ok || !same_sampling(s->gsp, *sp) || s->gnoise != noise) {
+            if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CAR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            int r = enqueue_decode_layers(s, s->logits, st);
+            if (r == CAR_OK) r = launch_sampler(a, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (r != CAR_OK) { if (g) cudaGraphDestroy(g); return r; }
+            if (ce != cudaSuccess) CAR_FAIL(CAR_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&s->gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) CAR_FAIL(CAR_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+            s->graph_ok = true; s->gsp = *sp; s->gnoise = noise;
+        }
+        const int per_step = s->m->d.n_layer * 5 + 2;
+        for (int i = 1; i < n_tokens; ++i) CAR_CUDA(cudaGraphLaunch(s->gexec, st));
+        g_car_launches.fetch_add((long long)per_step * (n_tokens - 1), std::memory_order_relaxed);
+    }
+    const int B = a.B;
+    CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, B,
+                               cudaMemcpyDeviceToDevice, st));
+    s->prefilled = false;
+    return CAR_OK;
+}
+
+extern "C" int64_t car_decode_step_bytes(const CarState* s, int32_t n_context) {
+    if (!s) return -1;
+    const CarModelDesc& d = s->m->d;
+    const int64_t es = d.dtype == CAR_BF16 ? 2 : 4;
+    const int64_t P = (int64_t)d.n_layer * (4LL * d.dim * d.dim + 3LL * d.dim * d.ffn_dim) + (int64_t)d.vocab_size * d.dim;
+    const int64_t kappa = 2LL * d.n_layer * d.dim * es;
+    return es * P + (int64_t)s->b_eff * kappa * n_context + (int64_t)s->b_eff * kappa + 4LL * s->b_eff * d.vocab_size;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// building-block ops for unit tests
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int car_op_linear(int32_t dtype, const void* x, const void* w, const void* bias, void* y, int32_t M, int32_t N,
+                             int32_t K, int32_t act, void* stream) {
+    if (!x || !w || !y) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    EpiParams e = epi_base(EPI_STORE);
+    e.out = y; e.ldo = N; e.act = act; e.bias = bias;
+    if (dtype == CAR_F32) return launch_skinny(st, dtype, x, K, w, nullptr, 0.f, M, N, K, e, false);
+    void* packed = nullptr;
+    CAR_CUDA(cudaMallocAsync(&packed, (size_t)N * K * 2, st));
+    const int nblk = N / 8;
+    const long long total = (long long)nblk * (K / 32) * 32;
+    CAR_LAUNCH(pack_weight_bf16_kernel, (int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st, (const bf16*)w,
+               (const bf16*)nullptr, (uint4*)packed, nblk, K, 0);
+    int r = launch_skinny(st, dtype, x, K, packed, nullptr, 0.f, M, N, K, e, false);
+    cudaFreeAsync(packed, st);
+    return r;
+}
+
+extern "C" int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void* y, int32_t M, int32_t K, float eps, void* stream) {
+    if (!x || !w || !y) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CAR_BF16) CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), M, 256, 0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, K, eps);
+    else CAR_LAUNCH((rmsnorm_rows_kernel<float>), M, 256, 0, st, (const float*)x, (const float*)w, (float*)y, K, eps);
+    return CAR_OK;
+}

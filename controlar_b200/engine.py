@@ -1,0 +1,240 @@
+"""Host-side handles over the C ABI (include/controlar_b200.h): packed model + per-generate() state.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libcontrolar_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import CarModelDesc, CarSampling, CarWeights, check, cur_stream, dtype_code
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("controlar_b200: tensor is not on a CUDA device (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("controlar_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _ptr_array(ts: List[torch.Tensor]):
+    arr = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = _ptr(t)
+    return arr
+
+
+class ARModelHandle:
+    """CarModel: GEMM-ready copies of the transformer weights (re-packed when the module's weights change)."""
+
+    def __init__(self, module):
+        self.lib = _lib.lib()
+        self.module = module
+        self.handle = C.c_void_p()
+        self.version = None
+        self._keep = None
+        self._build()
+
+    # the tensors whose storage the library borrows
+    def _weights(self):
+        m = self.module
+        layers = list(m.layers)
+        w = CarWeights()
+        keep = []
+
+        def P(t):
+            keep.append(t)
+            return _ptr(t.detach())
+        w.tok_embeddings = P(m.tok_embeddings.weight)
+        w.norm = P(m.norm.weight)
+        w.output = P(m.output.weight)
+        arrs = {}
+        for name, get in [("attention_norm", lambda b: b.attention_norm.weight), ("wqkv", lambda b: b.attention.wqkv.weight),
+                          ("wo", lambda b: b.attention.wo.weight), ("ffn_norm", lambda b: b.ffn_norm.weight),
+                          ("w1", lambda b: b.feed_forward.w1.weight), ("w3", lambda b: b.feed_forward.w3.weight),
+                          ("w2", lambda b: b.feed_forward.w2.weight)]:
+            ts = [get(b).detach() for b in layers]
+            keep.extend(ts)
+            arrs[name] = _ptr_array(ts)
+            setattr(w, name, C.cast(arrs[name], C.POINTER(C.c_void_p)))
+        if m.model_type == "t2i":
+            w.cap_fc1 = P(m.cls_embedding.cap_proj.fc1.weight)
+            w.cap_fc2 = P(m.cls_embedding.cap_proj.fc2.weight)
+        else:
+            w.label_table = P(m.cls_embedding.embedding_table.weight)
+        w.cond_fc1 = P(m.condition_mlp.cap_proj.fc1.weight)
+        w.cond_fc2 = P(m.condition_mlp.cap_proj.fc2.weight)
+        for j in range(3):
+            w.ctl_fc1[j] = P(m.condition_layers[j].fc1.weight)
+            w.ctl_fc2[j] = P(m.condition_layers[j].fc2.weight)
+        keep.append(arrs)
+        return w, keep
+
+    def _signature(self):
+        m = self.module
+        ps = [m.tok_embeddings.weight, m.output.weight, m.layers[0].attention.wqkv.weight]
+        return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in ps) + \
+            (sum(p._version for p in m.parameters()),)
+
+    def _build(self):
+        m = self.module
+        cfg = m.config
+        dt = m.tok_embeddings.weight.dtype
+        d = CarModelDesc(dtype=dtype_code(dt), dim=cfg.dim, n_layer=cfg.n_layer, n_head=cfg.n_head,
+                         ffn_dim=m.layers[0].feed_forward.w1.weight.shape[0], vocab_size=cfg.vocab_size,
+                         cls_token_num=cfg.cls_token_num, block_size=cfg.block_size,
+                         caption_dim=cfg.caption_dim if m.model_type == "t2i" else 0,
+                         model_type=1 if m.model_type == "t2i" else 0, norm_eps=cfg.norm_eps, rope_base=cfg.rope_base)
+        w, keep = self._weights()
+        if self.handle:
+            check(self.lib.car_model_destroy(self.handle), "car_model_destroy")
+            self.handle = C.c_void_p()
+        check(self.lib.car_model_create(C.byref(d), C.byref(w), cur_stream(), C.byref(self.handle)), "car_model_create")
+        self._keep = keep
+        self.version = self._signature()
+        self.dtype = dt
+        self.desc = d
+
+    def refresh(self):
+        """Re-create the packed copies if parameters were replaced / updated in place since the last pack."""
+        if self._signature() != self.version:
+            self._build()
+
+    def close(self):
+        if self.handle:
+            self.lib.car_model_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ARStateHandle:
+    """CarState: KV caches (PyTorch-owned, reference layout), control tokens, scratch, decode CUDA graph."""
+
+    def __init__(self, model: ARModelHandle, b_eff: int, S: int, N: int, k_caches, v_caches, rope: torch.Tensor):
+        self.lib = model.lib
+        self.model = model
+        self.b_eff, self.S, self.N = b_eff, S, N
+        self._keep = (list(k_caches), list(v_caches), rope)
+        self.handle = C.c_void_p()
+        ka, va = _ptr_array(self._keep[0]), _ptr_array(self._keep[1])
+        check(self.lib.car_state_create(model.handle, b_eff, S, N, C.cast(ka, C.POINTER(C.c_void_p)),
+                                        C.cast(va, C.POINTER(C.c_void_p)), _ptr(rope), C.byref(self.handle)),
+              "car_state_create")
+        self.V = model.desc.vocab_size
+        self.T = model.desc.cls_token_num
+
+    def set_emb_mask(self, emb_mask: Optional[torch.Tensor]):
+        if emb_mask is None:
+            check(self.lib.car_state_set_emb_mask(self.handle, None, cur_stream()), "car_state_set_emb_mask")
+            return
+        em = (emb_mask != 0).to(torch.int32).contiguous()
+        assert em.shape == (self.b_eff, self.T), (em.shape, self.b_eff, self.T)
+        check(self.lib.car_state_set_emb_mask(self.handle, _ptr(em), cur_stream()), "car_state_set_emb_mask")
+        self._mask_keep = em
+
+    def prefill(self, cond: torch.Tensor, condition: Optional[torch.Tensor], control_strength: float,
+                all_rows: bool) -> torch.Tensor:
+        dev = cond.device
+        if cond.dtype in (torch.int64, torch.int32):
+            cond = cond.to(torch.int32).contiguous()
+        else:
+            cond = cond.to(self.model.dtype).contiguous()
+        if condition is not None:
+            condition = condition.to(self.model.dtype).contiguous()
+            assert condition.shape[0] == self.b_eff and condition.shape[1] == self.N, condition.shape
+        shape = (self.b_eff, self.T, self.V) if all_rows else (self.b_eff, self.V)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+        check(self.lib.car_prefill(self.handle, _ptr(cond), _ptr(condition), float(control_strength), _ptr(out),
+                                   1 if all_rows else 0, cur_stream()), "car_prefill")
+        self._io_keep = (cond, condition)
+        return out
+
+    def decode_step(self, tok: torch.Tensor, pos: int) -> torch.Tensor:
+        tok = tok.reshape(-1).to(torch.int32).contiguous()
+        assert tok.numel() == self.b_eff
+        out = torch.empty((self.b_eff, self.V), dtype=torch.float32, device=tok.device)
+        check(self.lib.car_decode_step(self.handle, _ptr(tok), int(pos), _ptr(out), cur_stream()), "car_decode_step")
+        self._tok_keep = tok
+        return out
+
+    def generate(self, sp: CarSampling, n_tokens: int, noise: Optional[torch.Tensor], device) -> torch.Tensor:
+        B = self.b_eff // 2 if sp.cfg_scale > 1.0 else self.b_eff
+        out = torch.empty((B, n_tokens), dtype=torch.int32, device=device)
+        if noise is not None:
+            noise = noise.to(torch.float32).contiguous()
+            assert noise.shape == (n_tokens, B, self.V), noise.shape
+        check(self.lib.car_generate(self.handle, C.byref(sp), int(n_tokens), _ptr(noise), _ptr(out), cur_stream()),
+              "car_generate")
+        self._noise_keep = noise
+        return out
+
+    def step_bytes(self, n_context: int) -> int:
+        return int(self.lib.car_decode_step_bytes(self.handle, int(n_context)))
+
+    def close(self):
+        if self.handle:
+            self.lib.car_state_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_sampling(temperature=1.0, top_k=0, top_p=1.0, sample_logits=True, cfg_scale=1.0, cfg_interval=-1,
+                  seed=0) -> CarSampling:
+    return CarSampling(temperature=float(temperature), top_k=int(top_k or 0), top_p=float(top_p),
+                       sample_logits=1 if sample_logits else 0, cfg_scale=float(cfg_scale),
+                       cfg_interval=int(cfg_interval), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def sample(logits: torch.Tensor, sp: CarSampling, cfg_on: bool = True, step: int = 0,
+           noise: Optional[torch.Tensor] = None, return_probs: bool = False):
+    """generate.sample() + CFG combine on [b_eff, V] fp32 logits (car_sample)."""
+    lib = _lib.lib()
+    logits = logits.to(torch.float32).contiguous()
+    b_eff, V = logits.shape
+    B = b_eff // 2 if sp.cfg_scale > 1.0 else b_eff
+    idx = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    probs = torch.empty((B, V), dtype=torch.float32, device=logits.device) if return_probs else None
+    if noise is not None:
+        noise = noise.to(torch.float32).contiguous()
+    check(lib.car_sample(_ptr(logits), b_eff, V, C.byref(sp), 1 if cfg_on else 0, int(step), _ptr(noise), _ptr(idx),
+                         _ptr(probs), cur_stream()), "car_sample")
+    return (idx, probs) if return_probs else idx
+
+
+def op_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """y = act(x @ w.T + bias) through the library's GEMM (car_op_linear)."""
+    lib = _lib.lib()
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K).contiguous()
+    N = w.shape[0]
+    y = torch.empty((x2.shape[0], N), dtype=x.dtype, device=x.device)
+    check(lib.car_op_linear(dtype_code(x.dtype), _ptr(x2), _ptr(w.detach().contiguous()),
+                            _ptr(bias.detach().contiguous()) if bias is not None else None, _ptr(y), x2.shape[0], N, K,
+                            int(act), cur_stream()), "car_op_linear")
+    return y.reshape(*x.shape[:-1], N)
+
+
+def op_rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    lib = _lib.lib()
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K).contiguous()
+    y = torch.empty_like(x2)
+    check(lib.car_op_rmsnorm(dtype_code(x.dtype), _ptr(x2), _ptr(w.detach().contiguous()), _ptr(y), x2.shape[0], K,
+                             float(eps), cur_stream()), "car_op_rmsnorm")
+    return y.reshape(x.shape)

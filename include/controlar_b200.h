@@ -1,0 +1,150 @@
+/*
+ * controlar_b200.h — C ABI of the B200-native ControlAR conditional-decoding hot path.
+ *
+ * The reference (hustvl/ControlAR) has NO native/FFI layer: its boundary for this path is a pure-Python module
+ * API.  This header is therefore the boundary a maintainer binds *underneath* that Python API
+ * (ctypes stub in INTEGRATION.md); each entry point names the reference function(s) it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions cross the boundary, no torch types.
+ *   - every function returns 0 on success, <0 on error; car_last_error() gives the message (thread-local).
+ *   - all device pointers are CUDA device memory owned by the CALLER (PyTorch) unless stated; the library only
+ *     borrows them for the call, or until car_*_destroy for registered weights / KV caches.
+ *   - every op takes a cudaStream_t (as void*) and is asynchronous on it; the library never calls
+ *     cudaDeviceSynchronize and never allocates inside a decode step.
+ *   - handles are not thread-safe; distinct handles may be used from distinct threads.
+ *   - dtype codes: CAR_BF16 = 0, CAR_F32 = 1 (storage type of weights, activations and KV cache).
+ */
+#ifndef CONTROLAR_B200_H_
+#define CONTROLAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAR_BF16 0
+#define CAR_F32 1
+
+#define CAR_OK 0
+#define CAR_ERR_ARG (-1)
+#define CAR_ERR_CUDA (-2)
+#define CAR_ERR_UNSUPPORTED (-3)
+#define CAR_ERR_STATE (-4)
+
+typedef struct CarModel CarModel;   /* packed transformer weights          */
+typedef struct CarState CarState;   /* per-generate() state: caches, graph */
+
+/* Shape of gpt_t2i.ModelArgs that matters to the kernels (autoregressive/models/gpt_t2i.py:31-61). */
+typedef struct CarModelDesc {
+    int32_t dtype;          /* CAR_BF16 | CAR_F32 */
+    int32_t dim;            /* d        */
+    int32_t n_layer;        /* L, L % 3 == 0 (gpt_t2i.py:320,457) */
+    int32_t n_head;         /* H, head_dim = dim / n_head must be 64 */
+    int32_t ffn_dim;        /* F (gpt_t2i.py:204-209) */
+    int32_t vocab_size;     /* V */
+    int32_t cls_token_num;  /* T: 120 (t2i) or 1 (c2i) */
+    int32_t block_size;     /* g*g, RoPE table side g (gpt_t2i.py:380-383) */
+    int32_t caption_dim;    /* 2048 (t2i) ; 0 for c2i */
+    int32_t model_type;     /* 0 = c2i (LabelEmbedder), 1 = t2i (CaptionEmbedder) */
+    float   norm_eps;
+    float   rope_base;
+} CarModelDesc;
+
+/* Device pointers to the reference checkpoint tensors, nn.Linear layout [out, in] row-major, in `dtype`
+ * (state-dict keys in comments; SURVEY.md §8b "Checkpoint contract").  Arrays have n_layer entries. */
+typedef struct CarWeights {
+    const void* tok_embeddings;            /* tok_embeddings.weight            [V, d]   */
+    const void* norm;                      /* norm.weight                      [d]      */
+    const void* output;                    /* output.weight                    [V, d]   */
+    const void* const* attention_norm;     /* layers.i.attention_norm.weight   [d]      */
+    const void* const* wqkv;               /* layers.i.attention.wqkv.weight   [3d, d]  */
+    const void* const* wo;                 /* layers.i.attention.wo.weight     [d, d]   */
+    const void* const* ffn_norm;           /* layers.i.ffn_norm.weight         [d]      */
+    const void* const* w1;                 /* layers.i.feed_forward.w1.weight  [F, d]   */
+    const void* const* w3;                 /* layers.i.feed_forward.w3.weight  [F, d]   */
+    const void* const* w2;                 /* layers.i.feed_forward.w2.weight  [d, F]   */
+    const void* cap_fc1;                   /* cls_embedding.cap_proj.fc1.weight [d, caption_dim] (t2i) */
+    const void* cap_fc2;                   /* cls_embedding.cap_proj.fc2.weight [d, d]            (t2i) */
+    const void* label_table;               /* cls_embedding.embedding_table.weight [classes+1, d] (c2i) */
+    const void* cond_fc1;                  /* condition_mlp.cap_proj.fc1.weight [d, d] */
+    const void* cond_fc2;                  /* condition_mlp.cap_proj.fc2.weight [d, d] */
+    const void* ctl_fc1[3];                /* condition_layers.j.fc1.weight     [d, d] */
+    const void* ctl_fc2[3];                /* condition_layers.j.fc2.weight     [d, d] */
+} CarWeights;
+
+/* Sampling parameters of generate.sample()/top_k_top_p_filtering (autoregressive/models/generate.py:17-74)
+ * plus the CFG knobs of prefill()/decode_one_token() (generate.py:85-110). */
+typedef struct CarSampling {
+    float    temperature;
+    int32_t  top_k;          /* 0 = off */
+    float    top_p;          /* 1.0 = off */
+    int32_t  sample_logits;  /* 1 = multinomial (exponential race), 0 = arg-max (lowest index wins ties) */
+    float    cfg_scale;      /* > 1 => rows [B, 2B) are the unconditional half */
+    int32_t  cfg_interval;   /* -1 = always combine (generate.py:121-122) */
+    uint64_t seed;           /* Philox key for the in-kernel exponential noise */
+} CarSampling;
+
+const char* car_last_error(void);
+int car_version(void);
+
+/* ---- model: replaces Transformer.__init__/load_state_dict/.to() weight residency (gpt_t2i.py:310-389) ---- */
+int car_model_create(const CarModelDesc* desc, const CarWeights* weights, void* stream, CarModel** out);
+/* Re-pack after the caller changed the borrowed weights in place (optimizer step, load_state_dict). */
+int car_model_repack(CarModel* m, const CarWeights* weights, void* stream);
+int car_model_destroy(CarModel* m);
+
+/* ---- state: replaces Transformer.setup_caches (gpt_t2i.py:391-405) + the mask edit of generate()
+ *      (generate.py:184-193).  k_cache[i]/v_cache[i]: caller-allocated [b_eff, H, S, 64] in `dtype`
+ *      (the reference's KVCache layout, gpt_t2i.py:220-235) so that model.layers[i].attention.kv_cache stays
+ *      inspectable from Python.  emb_mask: int32 [b_eff, T] (1 = attend) or NULL (all ones). ---- */
+/*      rope_table: fp32 [T + block_size, 32, 2] (cos, sin) = precompute_freqs_cis_2d (gpt_t2i.py:506-519),
+ *      computed by the host shell with the same torch ops so the table is bit-identical; borrowed. */
+int car_state_create(CarModel* m, int32_t b_eff, int32_t max_seq /* S */, int32_t n_img_tokens /* N */,
+                     void* const* k_cache, void* const* v_cache, const float* rope_table, CarState** out);
+int car_state_set_emb_mask(CarState* s, const int32_t* emb_mask_dev, void* stream);
+int car_state_destroy(CarState* s);
+
+/* ---- prefill: Transformer.forward inference-prefill branch (gpt_t2i.py:433-442,455-470) ----
+ * cond:      t2i: [b_eff, T, caption_dim] in dtype;  c2i: int32 [b_eff] class ids.
+ * condition: adapter_mlp output [b_eff, N, d] in dtype, or NULL (no control).
+ * logits_out: fp32 [b_eff, T, V] when all_rows != 0 else [b_eff, V] (last prefix row only). */
+int car_prefill(CarState* s, const void* cond, const void* condition, float control_strength,
+                float* logits_out, int32_t all_rows, void* stream);
+
+/* ---- teacher-forced decode step: Transformer.forward KV-cache branch (gpt_t2i.py:444-470) ----
+ * tok: int32 [b_eff]; pos: sequence position of `tok` (T <= pos < S); logits_out fp32 [b_eff, V]. */
+int car_decode_step(CarState* s, const int32_t* tok, int32_t pos, float* logits_out, void* stream);
+
+/* ---- sampling: generate.sample() + CFG combine (generate.py:59-74,89-90,103-107) on fp32 logits
+ * [b_eff, V] -> idx int32 [B] (B = b_eff/2 when cfg_scale > 1).  probs_out (fp32 [B, V]) and noise
+ * (fp32 [B, V] Exp(1) draws; NULL = in-kernel Philox) are optional.  step is the Philox sub-stream index. */
+int car_sample(const float* logits, int32_t b_eff, int32_t V, const CarSampling* sp, int32_t cfg_on, int32_t step,
+               const float* noise, int32_t* idx_out, float* probs_out, void* stream);
+
+/* ---- device-side generation loop: generate()'s prefill-sample + decode_n_tokens (generate.py:113-131,
+ * 195-204).  Must follow car_prefill(...) on the same state.  Runs n_tokens sampling steps (the first one on
+ * the prefill logits) as a replayed CUDA graph with no host synchronisation; tokens_out int32 [B, n_tokens].
+ * noise: optional fp32 [n_tokens, B, V]. ---- */
+int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise,
+                 int32_t* tokens_out, void* stream);
+
+/* Algorithmic HBM bytes of one decode step at context length n (SURVEY.md §8d formula). */
+int64_t car_decode_step_bytes(const CarState* s, int32_t n_context);
+/* Number of kernels the library launched since the counter was last reset (bench.py "gpu_launches"). */
+int64_t car_launch_count(int32_t reset);
+
+/* ---- building-block ops, exposed for unit parity tests (tests/test_ops_gpu.py) ---- */
+/* y[M,N] = act(x[M,K] @ W[N,K]^T (+bias)); act: 0 none, 1 GELU-tanh (gpt_t2i.py:171), 2 GELU-erf. */
+int car_op_linear(int32_t dtype, const void* x, const void* w, const void* bias, void* y, int32_t M, int32_t N,
+                  int32_t K, int32_t act, void* stream);
+/* RMSNorm.forward (gpt_t2i.py:193-198). */
+int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void* y, int32_t M, int32_t K, float eps,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONTROLAR_B200_H_ */

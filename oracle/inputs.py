@@ -1,0 +1,35 @@
+"""TEST INFRASTRUCTURE — seeded synthetic inputs shared by tests/golden/make_golden.py, the tests and bench.py.
+
+Shapes follow SURVEY.md §8(d): T5 embeddings left-padded and zeroed like
+/root/reference/autoregressive/sample/sample_t2i.py:146-160; control maps in [-1, 1] with three identical
+channels like sample_t2i.py:119-141 (`2*(x/255-0.5)`, `.repeat(1,3,1,1)`).
+"""
+from __future__ import annotations
+
+import torch
+
+
+def text_inputs(T: int, caption_dim: int, B: int, seed: int, dtype=torch.float32, min_valid: int = 3):
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.randn(B, T, caption_dim, generator=g)
+    valid = torch.randint(min_valid, T + 1, (B,), generator=g)
+    masks = torch.zeros(B, T, dtype=torch.int64)
+    for b in range(B):
+        masks[b, T - int(valid[b]):] = 1          # left padding: valid tokens at the end
+    emb = emb * masks[:, :, None]
+    return emb.to(dtype), masks
+
+
+def class_inputs(num_classes: int, B: int, seed: int):
+    return torch.randint(0, num_classes, (B,), generator=torch.Generator().manual_seed(seed))
+
+
+def control_map(B: int, H: int, W: int, seed: int, kind: str, dtype=torch.float32):
+    """kind 'canny': Bernoulli(0.1) edges in {-1,+1}; otherwise a smooth random field in [-1,1]."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "canny":
+        m = (torch.rand(B, 1, H, W, generator=g) < 0.1).float()
+    else:
+        lo = torch.rand(B, 1, max(H // 16, 1), max(W // 16, 1), generator=g)
+        m = torch.nn.functional.interpolate(lo, size=(H, W), mode="bilinear", align_corners=False)
+    return (2 * (m - 0.5)).repeat(1, 3, 1, 1).to(dtype)

@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the REFERENCE ITSELF (read-only import from
+/root/reference) on CPU with procedural weights (oracle/weights.py).  Run from the repo root in the build
+container only:
+
+    python tests/golden/make_golden.py [case ...]
+
+The GPU box has no /root/reference; tests there only read tests/golden/*.pt.  Each fixture records the torch /
+transformers versions it was made with.  Weights are NOT stored: tests rebuild them from (spec, seed).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import contextlib
+import io
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)       # reference first: `autoregressive.*`, `tokenizer.*`, `utils.*` resolve to it
+
+import torch
+import transformers
+
+from oracle.weights import GPTSpec, make_gpt_state_dict, make_vq_state_dict, gpt_shapes, vq_shapes
+from oracle.inputs import text_inputs, class_inputs, control_map
+
+torch.set_grad_enabled(False)
+
+
+def math_sdpa():
+    """Force the math SDPA backend — the one the reference itself forces in decode (generate.py:120) — for
+    prefill too.  On CPU the default backend for bf16 is the fused flash kernel, whose internal rounding differs
+    from the math path by ~1e-3 relative (and from whatever backend a GPU run would pick); pinning the oracle
+    needs one defined arithmetic.  `*_defaultsdpa` fixtures keep the platform-default spread on record."""
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    return torch.backends.cuda.sdp_kernel(enable_flash=False, enable_mem_efficient=False, enable_math=True)
+
+
+def header():
+    return {"torch": str(torch.__version__), "transformers": str(transformers.__version__), "device": "cpu",
+            "generator": "tests/golden/make_golden.py"}
+
+
+@contextlib.contextmanager
+def fake_hf_cwd(adapter_size: str):
+    """dinov2_adapter.py:13 loads 'autoregressive/models/dinov2-{size}' relative to CWD."""
+    from transformers import Dinov2Config, Dinov2Model
+    hidden = 384 if adapter_size == "small" else 768
+    cfg = Dinov2Config(hidden_size=hidden, num_hidden_layers=12, num_attention_heads=hidden // 64, mlp_ratio=4,
+                       patch_size=14, image_size=518, layerscale_value=1.0, qkv_bias=True, layer_norm_eps=1e-6)
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "autoregressive", "models", f"dinov2-{adapter_size}")
+        os.makedirs(d)
+        Dinov2Model(cfg).save_pretrained(d)
+        os.chdir(tmp)
+        try:
+            yield
+        finally:
+            os.chdir(old)
+
+
+def build_ref_gpt(spec: GPTSpec, seed: int, dtype):
+    from autoregressive.models.gpt_t2i import Transformer, ModelArgs
+    with fake_hf_cwd(spec.adapter_size), contextlib.redirect_stdout(io.StringIO()):
+        m = Transformer(ModelArgs(dim=spec.dim, n_layer=spec.n_layer, n_head=spec.n_head,
+                                  multiple_of=spec.multiple_of, vocab_size=spec.vocab_size,
+                                  cls_token_num=spec.cls_token_num, block_size=spec.block_size,
+                                  caption_dim=spec.caption_dim, num_classes=spec.num_classes,
+                                  model_type=spec.model_type, adapter_size=spec.adapter_size,
+                                  condition_type=spec.condition_type))
+    sd = make_gpt_state_dict(spec, seed)
+    ref_sd = m.state_dict()
+    assert set(ref_sd.keys()) == set(sd.keys()), (set(ref_sd) ^ set(sd))
+    for k in sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    return m.to(dtype).eval()
+
+
+def ar_case(name: str, spec: GPTSpec, B: int, H: int, W: int, cfg_scale: float, cs: float, dtype, seed: int = 0,
+            logit_steps=(0, 1, 2, 7), sampled: bool = True, save_all_logits: bool = True, force_math: bool = True):
+    from autoregressive.models.generate import generate
+    import autoregressive.models.generate as G
+    m = build_ref_gpt(spec, seed, dtype)
+    N = (H // 16) * (W // 16)
+    if spec.model_type == "t2i":
+        cond, masks = text_inputs(spec.cls_token_num, spec.caption_dim, B, seed + 1, dtype)
+    else:
+        cond = class_inputs(spec.num_classes, B, seed + 1)
+        masks = None
+    cmap = control_map(B, H, W, seed + 2, "canny" if spec.condition_type in ("canny", "seg") else "depth", dtype)
+
+    # --- control encoder outputs (reference modules) ---
+    feat = m.adapter(cmap)                 # [B, N, C]   dinov2_adapter.py:26-29
+    ctrl_in = m.adapter_mlp(feat)          # [B, N, d]   generate.py:138
+
+    # --- teacher-forced logits via instrumented decode: record fp32 logits the model returns ---
+    rec = []
+    orig_forward = m.forward
+
+    def spy(*a, **k):
+        lg, loss = orig_forward(*a, **k)
+        rec.append(lg[:, -1].clone())
+        return lg, loss
+    m.forward = spy
+    ctx = math_sdpa() if force_math else contextlib.nullcontext()
+    with ctx:
+      greedy = generate(m, cond, N, emb_masks=masks, cfg_scale=cfg_scale, condition=cmap, control_strength=cs,
+                      temperature=1.0, top_k=0, top_p=1.0, sample_logits=False)
+    m.forward = orig_forward
+    raw = torch.stack(rec, dim=1)          # [B_eff, N, V] raw model logits along the greedy trajectory
+    out = {"header": header(), "prefill_sdpa": "math" if force_math else "platform default", "spec": spec.__dict__, "seed": seed, "dtype": str(dtype), "B": B, "H": H, "W": W,
+           "cfg_scale": cfg_scale, "control_strength": cs,
+           "inputs": "oracle.inputs: text_inputs/class_inputs(seed+1), control_map(seed+2)",
+           "emb_masks": masks, "adapter_out": feat, "ctrl_in": ctrl_in,
+           "greedy_tokens": greedy.clone(),
+           "logit_steps": list(logit_steps),
+           "raw_logits": None if save_all_logits else raw[:, list(logit_steps)].clone(),
+           "raw_logits_all": raw.to(dtype).clone() if save_all_logits else None,
+           "raw_logits_absmax": raw.abs().amax(dim=-1),
+           "raw_top2": torch.topk(raw, 2, dim=-1)[0]}
+    if sampled:
+        torch.manual_seed(1234)
+        with (math_sdpa() if force_math else contextlib.nullcontext()):
+          out["sampled_tokens"] = generate(m, cond, N, emb_masks=masks, cfg_scale=cfg_scale, condition=cmap,
+                                         control_strength=cs, temperature=1.0, top_k=100, top_p=1.0,
+                                         sample_logits=True).clone()
+        out["sampled_seed"] = 1234
+        out["sampled_top_k"] = 100
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    print(name, "greedy", tuple(greedy.shape), "raw", tuple(raw.shape), flush=True)
+
+
+def sampler_case():
+    import autoregressive.models.generate as G
+    g = torch.Generator().manual_seed(7)
+    logits = torch.randn(4, 1, 16384, generator=g) * 2.0
+    logits[0, 0, 5] = logits[0, 0, 9] = logits[0].max() + 1.0        # exact tie at the top
+    cases = []
+    for (temp, k, p) in [(1.0, 2000, 1.0), (0.7, 50, 1.0), (1.0, 0, 0.9), (1.3, 1000, 0.8), (1.0, 1, 1.0)]:
+        idx, probs = G.sample(logits.clone(), temperature=temp, top_k=k, top_p=p, sample_logits=False)
+        cases.append({"temperature": temp, "top_k": k, "top_p": p, "probs": probs.clone(),
+                      "kept": torch.isfinite(torch.log(probs)).sum(-1)})
+    torch.manual_seed(99)
+    idx_s, probs_s = G.sample(logits.clone(), temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True)
+    torch.save({"header": header(), "logits": logits, "cases": cases,
+                "multinomial_seed": 99, "multinomial_idx": idx_s}, os.path.join(OUT, "sampler.pt"))
+    print("sampler ok", flush=True)
+
+
+def vq_case():
+    from tokenizer.tokenizer_image.vq_model import VQ_models
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8)
+    sd = make_vq_state_dict(seed=3)
+    ref = vq.state_dict()
+    assert set(ref) == set(sd), set(ref) ^ set(sd)
+    for k in sd:
+        assert tuple(ref[k].shape) == tuple(sd[k].shape), k
+    vq.load_state_dict(sd)
+    vq.eval()
+    g = torch.Generator().manual_seed(11)
+    out = {"header": header(), "seed": 3}
+    for tag, (h, w) in {"sq": (8, 8), "mr": (4, 6)}.items():
+        codes = torch.randint(0, 16384, (2, h * w), generator=g)
+        img = vq.decode_code(codes, [2, 8, h, w])
+        out[f"codes_{tag}"] = codes
+        out[f"image_{tag}"] = img.clone()
+        quant, _, info = vq.encode(img.clamp(-1, 1))
+        out[f"enc_idx_{tag}"] = info[2].clone()
+        out[f"enc_quant_{tag}"] = quant.clone()
+        # pre-quantisation latent, to measure near-ties in the arg-min
+        z = vq.quant_conv(vq.encoder(img.clamp(-1, 1)))
+        out[f"enc_z_{tag}"] = z.clone()
+    torch.save(out, os.path.join(OUT, "vq16.pt"))
+    print("vq ok", flush=True)
+
+
+def dino_case():
+    from autoregressive.models.dinov2_adapter import Dinov2_Adapter
+    from oracle.weights import dinov2_shapes, _fill
+    out = {"header": header(), "seed": 5}
+    for size in ("small", "base"):
+        hidden = 384 if size == "small" else 768
+        sd = _fill(dinov2_shapes(hidden, prefix="model."), 5, 0.02)
+        for ctype in ("canny", "depth"):
+            with fake_hf_cwd(size), contextlib.redirect_stdout(io.StringIO()):
+                ad = Dinov2_Adapter(adapter_size=size, condition_type=ctype)
+            assert set(ad.state_dict()) == set(sd)
+            ad.load_state_dict(sd)
+            ad.eval()
+            for dt in (torch.float32, torch.bfloat16):
+                a = ad.to(dt)
+                for (H, W) in ((64, 96),) if size == "base" else ((128, 128), (64, 96)):
+                    x = control_map(2, H, W, 21, "canny" if ctype == "canny" else "depth", dt)
+                    y = a(x)
+                    key = f"{size}_{ctype}_{str(dt).split('.')[-1]}_{H}x{W}"
+                    out[key + "_out"] = y.clone()
+            ad.to(torch.float32)
+    torch.save(out, os.path.join(OUT, "dinov2.pt"))
+    print("dino ok", flush=True)
+
+
+SMALL = dict(dim=256, n_layer=6, n_head=4, vocab_size=2048)
+
+CASES = {
+    "t2i_small_bf16": lambda: ar_case("t2i_small_bf16", GPTSpec(**SMALL, cls_token_num=120, block_size=64,
+                                                                model_type="t2i"),
+                                      B=2, H=128, W=128, cfg_scale=4.0, cs=0.6, dtype=torch.bfloat16),
+    "t2i_small_fp32": lambda: ar_case("t2i_small_fp32", GPTSpec(**SMALL, cls_token_num=120, block_size=64,
+                                                                model_type="t2i"),
+                                      B=2, H=128, W=128, cfg_scale=4.0, cs=0.6, dtype=torch.float32),
+    "t2i_mr_bf16": lambda: ar_case("t2i_mr_bf16", GPTSpec(**SMALL, cls_token_num=120, block_size=144,
+                                                          model_type="t2i", condition_type="depth"),
+                                   B=1, H=128, W=192, cfg_scale=4.0, cs=1.0, dtype=torch.bfloat16),
+    "t2i_mr_tall_bf16": lambda: ar_case("t2i_mr_tall_bf16", GPTSpec(**SMALL, cls_token_num=120, block_size=144,
+                                                                    model_type="t2i", condition_type="depth"),
+                                        B=1, H=192, W=128, cfg_scale=1.0, cs=1.0, dtype=torch.bfloat16,
+                                        sampled=False),
+    "c2i_small_bf16": lambda: ar_case("c2i_small_bf16", GPTSpec(**SMALL, cls_token_num=1, block_size=64,
+                                                                model_type="c2i"),
+                                      B=2, H=128, W=128, cfg_scale=4.0, cs=1.0, dtype=torch.bfloat16),
+    "c2i_small_fp32": lambda: ar_case("c2i_small_fp32", GPTSpec(**SMALL, cls_token_num=1, block_size=64,
+                                                                model_type="c2i"),
+                                      B=2, H=128, W=128, cfg_scale=1.0, cs=1.0, dtype=torch.float32,
+                                      sampled=False),
+    "t2i_B_bf16": lambda: ar_case("t2i_B_bf16", GPTSpec(dim=768, n_layer=12, n_head=12, vocab_size=16384,
+                                                        cls_token_num=120, block_size=64, model_type="t2i"),
+                                  B=1, H=128, W=128, cfg_scale=4.0, cs=1.0, dtype=torch.bfloat16,
+                                  logit_steps=(0, 5), sampled=False, save_all_logits=False),
+    "t2i_small_bf16_defaultsdpa": lambda: ar_case("t2i_small_bf16_defaultsdpa",
+                                                  GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
+                                                  B=2, H=128, W=128, cfg_scale=4.0, cs=0.6, dtype=torch.bfloat16,
+                                                  sampled=False, save_all_logits=False, force_math=False),
+    "sampler": sampler_case,
+    "vq16": vq_case,
+    "dinov2": dino_case,
+}
+
+if __name__ == "__main__":
+    todo = sys.argv[1:] or list(CASES)
+    for c in todo:
+        CASES[c]()
