@@ -50,6 +50,7 @@ struct CarState {
     bool prefilled;
     // decode graph
     cudaGraphExec_t gexec;
+    cudaStream_t cap_stream;   // capture happens on a private stream (the legacy default stream cannot capture)
     bool graph_ok;
     CarSampling gsp;
     const float* gnoise;
@@ -232,7 +233,8 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     s->m = m; s->b_eff = b_eff; s->S = S; s->N = N; s->T = T;
     s->kc.assign(k_cache, k_cache + d.n_layer); s->vc.assign(v_cache, v_cache + d.n_layer);
     s->rope = rope_table; s->emb_mask = nullptr; s->has_ctrl = false; s->cs = 1.f; s->prefilled = false;
-    s->gexec = nullptr; s->graph_ok = false; s->gnoise = nullptr;
+    s->gexec = nullptr; s->graph_ok = false; s->gnoise = nullptr; s->cap_stream = nullptr;
+    if (cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; CAR_FAIL(CAR_ERR_CUDA, "cudaStreamCreateWithFlags failed"); }
     const size_t es = m->esize();
     const size_t dd = d.dim, F = d.ffn_dim, V = d.vocab_size;
     const size_t MP = (size_t)b_eff * T, MC = (size_t)b_eff * N;
@@ -271,6 +273,7 @@ extern "C" int car_state_set_emb_mask(CarState* s, const int32_t* emb_mask_dev, 
 extern "C" int car_state_destroy(CarState* s) {
     if (!s) return CAR_OK;
     if (s->gexec) cudaGraphExecDestroy(s->gexec);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (void* p : s->owned) if (p) cudaFree(p);
     delete s;
     return CAR_OK;
@@ -502,10 +505,12 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
         if (!s->graph_ok || !same_sampling(s->gsp, *sp) || s->gnoise != noise) {
             if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
             cudaGraph_t g = nullptr;
-            CAR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            int r = enqueue_decode_layers(s, s->logits, st);
-            if (r == CAR_OK) r = launch_sampler(a, st);
-            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            const long long launched_before = g_car_launches.load();   // captured nodes are not launches yet
+            CAR_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeRelaxed));
+            int r = enqueue_decode_layers(s, s->logits, s->cap_stream);
+            if (r == CAR_OK) r = launch_sampler(a, s->cap_stream);
+            cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &g);
+            g_car_launches.store(launched_before);
             if (r != CAR_OK) { if (g) cudaGraphDestroy(g); return r; }
             if (ce != cudaSuccess) CAR_FAIL(CAR_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
             ce = cudaGraphInstantiate(&s->gexec, g, 0);
