@@ -96,3 +96,6 @@ def dtype_code(dt) -> int:
 def cur_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+from . import vision as _vision  # noqa: E402,F401  (registers the car_dino_* / car_vq_* prototypes in PROTOTYPES)

@@ -19,12 +19,12 @@ template <> struct RowLanes<float> { static constexpr int LPR = 16, EPL = 4; };
 
 template <typename T> __device__ __forceinline__ void load_row_frag(const T* p, float (&f)[RowLanes<T>::EPL]);
 template <> __device__ __forceinline__ void load_row_frag<bf16>(const bf16* p, float (&f)[8]) {
-    const uint4 v = ldg_stream(p);
+    const uint4 v = ldg_cg128(p);
     unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
     unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
 }
 template <> __device__ __forceinline__ void load_row_frag<float>(const float* p, float (&f)[4]) {
-    const uint4 v = ldg_stream(p);
+    const uint4 v = ldg_cg128(p);
     f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
 }
 
@@ -32,10 +32,10 @@ template <> __device__ __forceinline__ void load_row_frag<float>(const float* p,
 // The last CTA to finish a (b,h) combines the nsplit partials in index order (deterministic) and writes
 // out[b][h*64 + e] rounded to T (the SDPA output cast).
 template <typename T>
-__global__ void __launch_bounds__(AD_THREADS)
+__global__ void __launch_bounds__(AD_THREADS, 6)
 attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
                    const int* __restrict__ emb_mask, int mask_ld, const int* __restrict__ pos_ptr, int H, int S,
-                   int Tpre, int nsplit, float* __restrict__ part, int* __restrict__ tickets, T* __restrict__ out) {
+                   int Tpre, int nsplit, int flags, float* __restrict__ part, int* __restrict__ tickets, T* __restrict__ out) {
     constexpr int LPR = RowLanes<T>::LPR, EPL = RowLanes<T>::EPL, RPW = 32 / LPR;
     constexpr int UNR = 4;
     __shared__ float sm_m[AD_WARPS * RPW], sm_l[AD_WARPS * RPW];
@@ -46,16 +46,27 @@ attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* _
     const int split = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane / LPR, cl = lane % LPR;          // row slot within the warp, column chunk
-    const int pos = *pos_ptr, n = pos + 1;
+    // `pos` is only ever advanced by the sampler, which never triggers its dependents early, so it is stable for
+    // every kernel of the step — including before pdl_wait().
+    pdl_launch_dependents();
+    const int pos = ld_cg(pos_ptr), n = pos + 1;
     int chunk = (n + nsplit - 1) / nsplit;
     chunk = (chunk + 7) & ~7;
     const int k0 = split * chunk, k1 = min(n, k0 + chunk);
+    // pull this CTA's slice of the cache towards L2 while the QKV GEMM is still running (rows < pos are final)
+    if (flags & 1) {
+        const char* kb = reinterpret_cast<const char*>(kc + ((size_t)bh * S + k0) * 64);
+        const char* vb = reinterpret_cast<const char*>(vc + ((size_t)bh * S + k0) * 64);
+        const int lines = max(0, min(k1, pos) - k0) * 64 * (int)sizeof(T) / 128;
+        for (int i = tid; i < lines; i += AD_THREADS) { prefetch_l2(kb + (size_t)i * 128); prefetch_l2(vb + (size_t)i * 128); }
+    }
+    pdl_wait();
 
     float qf[EPL];
     {
         const T* qp = q + (size_t)b * H * 64 + hd * 64 + cl * EPL;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) qf[e] = tof(qp[e]);
+        for (int e = 0; e < EPL; ++e) qf[e] = ld_cg(qp + e);
     }
     const T* kbase = kc + ((size_t)bh * S) * 64 + cl * EPL;
     const T* vbase = vc + ((size_t)bh * S) * 64 + cl * EPL;

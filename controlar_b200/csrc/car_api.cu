@@ -2,6 +2,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 
 #include "common.cuh"
@@ -12,6 +13,23 @@
 
 thread_local std::string g_car_err;
 std::atomic<long long> g_car_launches{0};
+
+// development knobs (environment, read once): CAR_PDL, CAR_L2PF, CAR_NSPLIT, CAR_NB_QKV/WO/W13/W2/HEAD
+struct Tune { int pdl, l2pf, nsplit, nb[5], skip, empty, dbg; };
+static long long* g_dbg = nullptr;   // [5 kernels][8] clock stamps (CAR_DBG=1)
+__global__ void empty_kernel(int) {}
+static const Tune& tune() {
+    static Tune t = [] {
+        Tune x;
+        auto gi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
+        x.dbg = gi("CAR_DBG", 0); x.skip = gi("CAR_SKIP", 0); x.empty = gi("CAR_EMPTY", 0);
+        x.pdl = gi("CAR_PDL", 1); x.l2pf = gi("CAR_L2PF", 1); x.nsplit = gi("CAR_NSPLIT", 0);
+        x.nb[EPI_STORE] = 0; x.nb[EPI_QKV] = gi("CAR_NB_QKV", 0); x.nb[EPI_RESID] = gi("CAR_NB_RESID", 0);
+        x.nb[EPI_SWIGLU] = gi("CAR_NB_W13", 0); x.nb[EPI_LOGITS] = gi("CAR_NB_HEAD", 0);
+        return x;
+    }();
+    return t;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // structures
@@ -81,11 +99,21 @@ static int launch_skinny_bf16_inst(cudaStream_t st, const bf16* A, int lda, cons
     const size_t smem = skinny_smem_bytes(K, NB);
     if (!attr_set) {
         CAR_CUDA(cudaFuncSetAttribute(skinny_gemm_bf16<NB, U, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CAR_CUDA(cudaFuncSetAttribute(skinny_gemm_bf16<NB, U, NORM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     if (smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "K too large for the shared-memory activation tile");
     dim3 grid((nblk + NB - 1) / NB, (M + 15) / 16);
-    CAR_LAUNCH((skinny_gemm_bf16<NB, U, NORM>), grid, SK_THREADS, smem, st, A, lda, (const uint4*)Wp, nw, eps, K, nblk, ep);
+    if (grid.y == 1) {   // decode shape: never more than one wave of CTAs; a CTA strides over its column groups
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_gemm_bf16<NB, U, NORM>, SK_THREADS, smem);
+        const unsigned cap = 148u * (unsigned)std::max(1, std::min(occ, 2));
+        if (grid.x > cap) grid.x = cap;
+    }
+    const int flags = tune().l2pf ? 1 : 0;
+    if (tune().empty) { CAR_LAUNCH(empty_kernel, grid, SK_THREADS, smem, st, 0); return CAR_OK; }
+    if (tune().pdl) CAR_LAUNCH_PDL((skinny_gemm_bf16<NB, U, NORM>), grid, dim3(SK_THREADS), smem, st, A, lda, (const uint4*)Wp, nw, eps, K, nblk, flags, ep);
+    else CAR_LAUNCH((skinny_gemm_bf16<NB, U, NORM>), grid, SK_THREADS, smem, st, A, lda, (const uint4*)Wp, nw, eps, K, nblk, flags, ep);
     return CAR_OK;
 }
 
@@ -93,9 +121,10 @@ template <int NB, bool NORM>
 static int launch_skinny_bf16_u(cudaStream_t st, int U, const bf16* A, int lda, const void* Wp, const bf16* nw, float eps,
                                 int M, int nblk, int K, const EpiParams& ep) {
     switch (U) {
-        case 5: return launch_skinny_bf16_inst<NB, 5, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
-        case 7: return launch_skinny_bf16_inst<NB, 7, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
-        default: return launch_skinny_bf16_inst<NB, 4, NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        case 5: if (NB <= 2) return launch_skinny_bf16_inst<NB, (NB <= 2 ? 5 : 4), NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        case 7: if (NB <= 2) return launch_skinny_bf16_inst<NB, (NB <= 2 ? 7 : 4), NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        case 2: if (NB == 8) return launch_skinny_bf16_inst<NB, (NB == 8 ? 2 : 4), NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
+        default: return launch_skinny_bf16_inst<NB, (NB == 8 ? 2 : 4), NORM>(st, A, lda, Wp, nw, eps, M, nblk, K, ep);
     }
 }
 
@@ -119,17 +148,18 @@ static int launch_skinny(cudaStream_t st, int dtype, const void* A, int lda, con
     int NB;
     if (mtiles > 1) NB = 4;                       // M-tiled (prefill): maximise reuse of the activation tile
     else {
-        const int want = nblk / 148;              // aim at >= one CTA per SM
-        NB = want >= 4 ? 4 : (want >= 2 ? 2 : 1);
-        const bool big_tile = skinny_smem_bytes(K, 1) > 100 * 1024;   // one CTA per SM: avoid a 2nd partial wave
-        if (big_tile && nblk > 148 && NB == 1) NB = 2;
+        // one wave: ceil(nblk / NB) <= 148 where possible (register use makes these 1 CTA / SM kernels)
+        const int want = (nblk + 147) / 148;
+        NB = want > 4 ? 8 : (want > 2 ? 4 : (want > 1 ? 2 : 1));
     }
+    if (mtiles == 1 && tune().nb[ep.kind] > 0) NB = tune().nb[ep.kind];
     if (ep.kind == EPI_SWIGLU && NB == 1) NB = 2;
-    if (NB * U > 16) U = 4;                       // register budget
+    if (NB == 8) U = 2; else if (NB * U > 16) U = 4;   // register budget
     const bf16* Ab = (const bf16*)A; const bf16* nwb = (const bf16*)nw;
 #define CAR_SK(NB_) (norm ? launch_skinny_bf16_u<NB_, true>(st, U, Ab, lda, W, nwb, eps, M, nblk, K, ep) \
                           : launch_skinny_bf16_u<NB_, false>(st, U, Ab, lda, W, nwb, eps, M, nblk, K, ep))
     switch (NB) {
+        case 8: return CAR_SK(8);
         case 4: return CAR_SK(4);
         case 2: return CAR_SK(2);
         default: return CAR_SK(1);
@@ -239,6 +269,7 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     const size_t dd = d.dim, F = d.ffn_dim, V = d.vocab_size;
     const size_t MP = (size_t)b_eff * T, MC = (size_t)b_eff * N;
     s->nsplit = std::max(1, std::min(16, (4 * 148 + b_eff * d.n_head - 1) / (b_eff * d.n_head)));
+    if (tune().nsplit > 0) s->nsplit = std::min(32, tune().nsplit);
     int r = CAR_OK;
     auto A = [&](void** p, size_t bytes) { if (r == CAR_OK) r = alloc_dev(s->owned, p, bytes); };
     A(&s->h, b_eff * dd * es); A(&s->q, b_eff * dd * es); A(&s->attn, b_eff * dd * es); A(&s->act, b_eff * F * es);
@@ -286,9 +317,15 @@ template <typename T>
 static int launch_attn_decode(CarState* s, int l, cudaStream_t st) {
     const CarModelDesc& d = s->m->d;
     dim3 grid(s->b_eff * d.n_head, s->nsplit);
-    CAR_LAUNCH((attn_decode_kernel<T>), grid, AD_THREADS, 0, st, (const T*)s->q, (const T*)s->kc[l], (const T*)s->vc[l],
-               (const int*)s->emb_mask, s->T, (const int*)s->pos, d.n_head, s->S, s->T, s->nsplit, s->attn_part, s->tickets,
-               (T*)s->attn);
+    const int flags = tune().l2pf ? 1 : 0;
+    if (tune().pdl)
+        CAR_LAUNCH_PDL((attn_decode_kernel<T>), grid, dim3(AD_THREADS), 0, st, (const T*)s->q, (const T*)s->kc[l], (const T*)s->vc[l],
+                       (const int*)s->emb_mask, s->T, (const int*)s->pos, d.n_head, s->S, s->T, s->nsplit, flags, s->attn_part,
+                       s->tickets, (T*)s->attn);
+    else
+        CAR_LAUNCH((attn_decode_kernel<T>), grid, AD_THREADS, 0, st, (const T*)s->q, (const T*)s->kc[l], (const T*)s->vc[l],
+                   (const int*)s->emb_mask, s->T, (const int*)s->pos, d.n_head, s->S, s->T, s->nsplit, flags, s->attn_part,
+                   s->tickets, (T*)s->attn);
     return CAR_OK;
 }
 
@@ -325,18 +362,25 @@ static int enqueue_block(CarState* s, int l, bool decode, cudaStream_t st) {
     EpiParams e1 = epi_base(EPI_QKV);
     e1.rpb = rpb; e1.pos_ptr = posp; e1.rope = s->rope; e1.kc = s->kc[l]; e1.vc = s->vc[l]; e1.q = q; e1.S = s->S;
     e1.H = d.n_head; e1.d = dim;
-    CAR_TRY(launch_skinny(st, dt, h, dim, m->g_wqkv[l], m->attention_norm[l], d.norm_eps, rows, 3 * dim, dim, e1, true));
+    const int skip = decode ? tune().skip : 0;
+    if (tune().dbg && decode && l == 3) {
+        if (!g_dbg) { cudaMalloc(&g_dbg, 5 * 8 * 8); cudaMemset(g_dbg, 0, 5 * 8 * 8); }
+        e1.dbg = g_dbg;
+    }
+    if (!(skip & 1)) CAR_TRY(launch_skinny(st, dt, h, dim, m->g_wqkv[l], m->attention_norm[l], d.norm_eps, rows, 3 * dim, dim, e1, true));
 
-    if (decode) { if (dt == CAR_BF16) CAR_TRY(launch_attn_decode<bf16>(s, l, st)); else CAR_TRY(launch_attn_decode<float>(s, l, st)); }
+    if (decode) { if (!(skip & 2)) { if (dt == CAR_BF16) CAR_TRY(launch_attn_decode<bf16>(s, l, st)); else CAR_TRY(launch_attn_decode<float>(s, l, st)); } }
     else { if (dt == CAR_BF16) CAR_TRY(launch_attn_prefill<bf16>(s, l, st)); else CAR_TRY(launch_attn_prefill<float>(s, l, st)); }
 
     EpiParams e2 = epi_base(EPI_RESID);
     e2.rpb = rpb; e2.pos_ptr = posp; e2.h = h; e2.ldh = dim;
-    CAR_TRY(launch_skinny(st, dt, attn, dim, m->g_wo[l], nullptr, 0.f, rows, dim, dim, e2, false));
+    if (tune().dbg && decode && l == 3) e2.dbg = g_dbg + 8;
+    if (!(skip & 4)) CAR_TRY(launch_skinny(st, dt, attn, dim, m->g_wo[l], nullptr, 0.f, rows, dim, dim, e2, false));
 
     EpiParams e3 = epi_base(EPI_SWIGLU);
     e3.rpb = rpb; e3.out = act; e3.ldo = F;
-    CAR_TRY(launch_skinny(st, dt, h, dim, m->g_w13[l], m->ffn_norm[l], d.norm_eps, rows, 2 * F, dim, e3, true));
+    if (tune().dbg && decode && l == 3) e3.dbg = g_dbg + 16;
+    if (!(skip & 8)) CAR_TRY(launch_skinny(st, dt, h, dim, m->g_w13[l], m->ffn_norm[l], d.norm_eps, rows, 2 * F, dim, e3, true));
 
     EpiParams e4 = epi_base(EPI_RESID);
     e4.rpb = rpb; e4.pos_ptr = posp; e4.h = h; e4.ldh = dim;
@@ -345,7 +389,8 @@ static int enqueue_block(CarState* s, int l, bool decode, cudaStream_t st) {
         // control add of the NEXT layer group fused here (gpt_t2i.py:466)
         e4.ctrl = s->ctrl[(l + 1) / step3]; e4.n_img = s->N; e4.T = s->T; e4.cs = s->cs;
     }
-    CAR_TRY(launch_skinny(st, dt, act, F, m->g_w2[l], nullptr, 0.f, rows, dim, F, e4, false));
+    if (tune().dbg && decode && l == 3) e4.dbg = g_dbg + 24;
+    if (!(skip & 16)) CAR_TRY(launch_skinny(st, dt, act, F, m->g_w2[l], nullptr, 0.f, rows, dim, F, e4, false));
     return CAR_OK;
 }
 
@@ -458,6 +503,7 @@ static int launch_sampler(const SampleArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const size_t smem = (size_t)a.V * 4;
@@ -526,6 +572,17 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
     CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, B,
                                cudaMemcpyDeviceToDevice, st));
     s->prefilled = false;
+    if (tune().dbg && g_dbg) {
+        cudaStreamSynchronize(st);
+        long long hbuf[40];
+        cudaMemcpy(hbuf, g_dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        const char* names[4] = {"qkv", "wo", "w13", "w2"};
+        for (int k = 0; k < 4; ++k) {
+            long long* t = hbuf + 8 * k;
+            fprintf(stderr, "[dbg] %-4s wait %6lld | stage %6lld | main %6lld | reduce %6lld | epi %6lld | total %6lld cycles\n", names[k],
+                    t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[5] - t[0]);
+        }
+    }
     return CAR_OK;
 }
 

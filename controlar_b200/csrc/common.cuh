@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <string>
+#include <cstring>
 
 #include "../../include/controlar_b200.h"
 
@@ -48,6 +49,45 @@ extern std::atomic<long long> g_car_launches;
             return CAR_ERR_CUDA;                                                                    \
         }                                                                                           \
     } while (0)
+
+// Programmatic dependent launch (PDL): the next kernel in the stream is launched while this one still runs; its
+// prologue (weight loads / L2 prefetch of immutable data) overlaps our tail, and it blocks in pdl_wait() until
+// this grid has completed and its writes are visible.  Rule: nothing mutable may be touched before pdl_wait().
+#define CAR_LAUNCH_PDL(kernel, grid_, block_, smem_, strm_, ...)                                      \
+    do {                                                                                            \
+        cudaLaunchConfig_t _cfg;                                                                    \
+        memset(&_cfg, 0, sizeof(_cfg));                                                             \
+        _cfg.gridDim = (grid_); _cfg.blockDim = (block_); _cfg.dynamicSmemBytes = (smem_); _cfg.stream = (strm_); \
+        cudaLaunchAttribute _at[1];                                                                 \
+        _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                             \
+        _at[0].val.programmaticStreamSerializationAllowed = 1;                                      \
+        _cfg.attrs = _at; _cfg.numAttrs = 1;                                                        \
+        cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                            \
+        g_car_launches.fetch_add(1, std::memory_order_relaxed);                                     \
+        if (_e != cudaSuccess) {                                                                    \
+            g_car_err = std::string(__func__) + ": launch " #kernel " -> " + cudaGetErrorString(_e); \
+            return CAR_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// mutable data (activations, KV cache, device scalars) is always read through L2 (.cg): with PDL a dependent
+// kernel's CTAs are resident before the producer finishes, so an L1 line could otherwise be stale.
+__device__ __forceinline__ uint4 ldg_cg128(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float ld_cg(const bf16* p) {
+    unsigned short v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __uint_as_float(((uint32_t)v) << 16);
+}
+__device__ __forceinline__ int ld_cg(const int* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------------------------------------------------
 // storage-type helpers: all arithmetic is fp32; `rnd<T>` marks the points where eager PyTorch would

@@ -31,6 +31,7 @@ struct EpiParams {
     const float* rope; void* kc; void* vc; void* q; int S; int H; int d;
     // EPI_LOGITS
     float* logits; long long ldl;
+    long long* dbg;       // dev instrumentation: per-phase clock64 stamps of CTA 0 (null in production)
 };
 
 // tile: [16][ldt] fp32 accumulators for columns [nb0*8, nb0*8 + ncols) of rows [m0, m0+16)
@@ -56,7 +57,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& ep, const float* t
         const int n = nb0 * 8 + c;
         float v0 = tile[m * ldt + c], v1 = tile[m * ldt + c + 1];
         const int b = r / ep.rpb;
-        const int pos = ep.pos_ptr ? *ep.pos_ptr : (r - b * ep.rpb);
+        const int pos = ep.pos_ptr ? ld_cg(ep.pos_ptr) : (r - b * ep.rpb);
         switch (ep.kind) {
             case EPI_STORE: {
                 if (ep.bias) { v0 += tof(((const T*)ep.bias)[n]); v1 += tof(((const T*)ep.bias)[n + 1]); }
@@ -68,8 +69,8 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& ep, const float* t
             } break;
             case EPI_RESID: {
                 T* hp = (T*)ep.h + (size_t)r * ep.ldh + n;
-                float o0 = rnd<T>(tof(hp[0]) + rnd<T>(v0));
-                float o1 = rnd<T>(tof(hp[1]) + rnd<T>(v1));
+                float o0 = rnd<T>(ld_cg(hp) + rnd<T>(v0));
+                float o1 = rnd<T>(ld_cg(hp + 1) + rnd<T>(v1));
                 if (ep.ctrl) {   // gpt_t2i.py:466 — h += cs * ctrl[:, pos - T + 1] ahead of the next layer group
                     const int p = pos - ep.T + 1;
                     if (p >= 0 && p < ep.n_img) {
@@ -113,14 +114,14 @@ constexpr int SK_WARPS = 8;
 constexpr int SK_THREADS = SK_WARPS * 32;
 
 static inline size_t skinny_smem_bytes(int K, int NB) {
-    return (size_t)16 * (K + 32) * 2 + (size_t)SK_WARPS * NB * 128 * 4;
+    return (size_t)16 * (K + 32) * 2 + (size_t)SK_WARPS * NB * 128 * 4 + (size_t)16 * NB * 8 * 4;
 }
 
 // grid = (ceil(nblk/NB), ceil(M/16)); Wp: packed weights, chunk (nb, s) at ((nb*(K/32)+s)*32 + lane) uint4
 template <int NB, int U, bool NORM>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ Wp, const bf16* __restrict__ nw,
-                 float eps, int K, int nblk, EpiParams ep) {
+                 float eps, int K, int nblk, int flags, EpiParams ep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KS = K + 32;                                  // bf16 elements per smem row (+64 B: conflict-free)
     bf16* As = reinterpret_cast<bf16*>(smem_raw);
@@ -129,10 +130,12 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int m0 = blockIdx.y * 16;
     const int mrows = min(16, ep.M - m0);
-    const int nb0 = blockIdx.x * NB;
+    int nb0 = blockIdx.x * NB;
     const int ksteps = K >> 5;
     const int nsteps = (ksteps - warp + SK_WARPS - 1) / SK_WARPS;   // k32-steps owned by this warp: warp, warp+8, ..
 
+    const bool dbg_on = ep.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    if (dbg_on) ep.dbg[0] = clock64();
     // ---- 1. first batch of weight fragments in flight before anything that depends on the previous kernel
     uint4 wf[U][NB];
     auto load_batch = [&](int i0) {
@@ -148,11 +151,23 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
             }
         }
     };
+    pdl_launch_dependents();
     load_batch(0);
+    // the rest of this warp's weight stream goes to L2 now, so the post-dependency loop never waits on HBM
+    for (int i = U; (flags & 1) && i < nsteps; ++i) {
+        const int s = warp + i * SK_WARPS;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            if (nb0 + j < nblk && (lane & 7) == 0)
+                prefetch_l2(Wp + ((size_t)(nb0 + j) * ksteps + s) * 32 + lane);
+    }
+    pdl_wait();   // ---- everything below may read what the previous kernel wrote
+    if (dbg_on) ep.dbg[1] = clock64();
 
-    // ---- 2. stage the 16-row activation tile (RMSNorm fused when NORM)
+    // ---- 2. stage the 16-row activation tile (RMSNorm fused when NORM): one pass over global memory
     const int chunks = K >> 3;   // 16-byte chunks per row
     if (NORM) {
+        constexpr int MAXC = 8;                       // register-held chunks per lane (K <= 2048)
         for (int rr = warp; rr < 16; rr += SK_WARPS) {
             bf16* dst = As + (size_t)rr * KS;
             if (rr >= mrows) {
@@ -160,19 +175,26 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
                 continue;
             }
             const bf16* src = A + (size_t)(m0 + rr) * lda;
+            uint4 held[MAXC];
             float ss = 0.f;
-            for (int c = lane; c < chunks; c += 32) {
-                const uint4 v = *reinterpret_cast<const uint4*>(src + c * 8);
+            auto sq = [&](const uint4& v) {
                 float a, b;
                 unpack_bf16x2(v.x, a, b); ss += a * a + b * b;
                 unpack_bf16x2(v.y, a, b); ss += a * a + b * b;
                 unpack_bf16x2(v.z, a, b); ss += a * a + b * b;
                 unpack_bf16x2(v.w, a, b); ss += a * a + b * b;
+            };
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) {
+                const int c = lane + 32 * ci;
+                held[ci] = c < chunks ? ldg_cg128(src + c * 8) : make_uint4(0, 0, 0, 0);
             }
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) sq(held[ci]);
+            for (int c = lane + 32 * MAXC; c < chunks; c += 32) sq(ldg_cg128(src + c * 8));   // K > 2048 tail
             ss = warp_sum(ss);
             const float rstd = rsqrtf(ss / (float)K + eps);
-            for (int c = lane; c < chunks; c += 32) {
-                const uint4 v = *reinterpret_cast<const uint4*>(src + c * 8);
+            auto norm_store = [&](const uint4& v, int c) {
                 const uint4 wv = *reinterpret_cast<const uint4*>(nw + c * 8);
                 const uint32_t xi[4] = {v.x, v.y, v.z, v.w};
                 const uint32_t wi[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -189,7 +211,13 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
                     o[q] = *reinterpret_cast<uint32_t*>(&pk);
                 }
                 *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            };
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) {
+                const int c = lane + 32 * ci;
+                if (c < chunks) norm_store(held[ci], c);
             }
+            for (int c = lane + 32 * MAXC; c < chunks; c += 32) norm_store(ldg_cg128(src + c * 8), c);
         }
     } else {
         for (int idx = tid; idx < 16 * chunks; idx += SK_THREADS) {
@@ -202,7 +230,12 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
     }
     __syncthreads();
 
-    // ---- 3. main loop: this warp's k-steps, all NB column blocks
+    if (dbg_on) ep.dbg[2] = clock64();
+    // ---- 3. main loop: this warp's k-steps, all NB column blocks; the CTA then strides to its next column group
+    // (grid.x is capped at one wave, the staged activation tile is reused)
+    float* tile = reinterpret_cast<float*>(smem_raw + (size_t)16 * KS * 2 + (size_t)SK_WARPS * NB * 128 * 4);   // [16][NB*8]
+  for (bool first = true; nb0 < nblk; nb0 += gridDim.x * NB, first = false) {
+    if (!first) load_batch(0);
     float acc[NB][4];
 #pragma unroll
     for (int j = 0; j < NB; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
@@ -225,6 +258,7 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
         }
     }
 
+    if (dbg_on && first) ep.dbg[3] = clock64();
     // ---- 4. cross-warp K reduction in fixed order, then the fused epilogue
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -235,7 +269,6 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
         rp[(g + 8) * 8 + 2 * t + 1] = acc[j][3];
     }
     __syncthreads();
-    float* tile = reinterpret_cast<float*>(smem_raw);   // reuse the A region: [16][NB*8]
     for (int idx = tid; idx < NB * 128; idx += SK_THREADS) {
         const int j = idx >> 7, e = idx & 127;
         float s = 0.f;
@@ -244,8 +277,11 @@ skinny_gemm_bf16(const bf16* __restrict__ A, int lda, const uint4* __restrict__ 
         tile[(e >> 3) * (NB * 8) + j * 8 + (e & 7)] = s;
     }
     __syncthreads();
+    if (dbg_on && first) ep.dbg[4] = clock64();
     const int ncols = min(NB, nblk - nb0) * 8;
     run_epilogue<bf16>(ep, tile, NB * 8, m0, nb0, ncols, tid, SK_THREADS);
+    if (dbg_on && first) ep.dbg[5] = clock64();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

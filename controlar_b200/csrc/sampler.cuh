@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = a.V;
-    const int pos = a.pos_ptr ? *a.pos_ptr : 0;
+    const int pos = a.pos_ptr ? ld_cg(a.pos_ptr) : 0;
     const int step = a.pos_ptr ? (pos - a.T + 1) : a.step;   // index of the token being produced
     bool cfg_on = a.cfg_on != 0;
     if (a.cfg_interval > -1 && step - 1 > a.cfg_interval) cfg_on = false;
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
     const float* lc = a.logits + (size_t)b * V;
     const float* lu = a.logits + (size_t)(b + a.B) * V;
     for (int i = tid; i < V; i += SMP_THREADS) {
-        float v = lc[i];
-        if (a.use_cfg && cfg_on) { const float u = lu[i]; v = u + (v - u) * a.cfg_scale; }
+        float v = __ldcg(lc + i);
+        if (a.use_cfg && cfg_on) { const float u = __ldcg(lu + i); v = u + (v - u) * a.cfg_scale; }
         z[i] = v * a.inv_temp;
     }
     __syncthreads();

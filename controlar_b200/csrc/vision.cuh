@@ -1,0 +1,273 @@
+// vision.cuh — normalisation / resampling / soft-max / quantiser kernels around the dense GEMM for the control
+// encoder (HF Dinov2Model as used by autoregressive/models/dinov2_adapter.py) and the VQGAN tokenizer
+// (tokenizer/tokenizer_image/vq_model.py).
+#pragma once
+#include "common.cuh"
+
+// ---- block reduce helpers (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) s = fmaxf(s, red[i]);
+    __syncthreads();
+    return s;
+}
+
+// nn.LayerNorm over the last dim (fp32 statistics, eps inside the sqrt), bf16 in/out.  one block per row.
+__global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                 bf16* __restrict__ y, int C, float eps, long long in_stride, long long out_stride) {
+    __shared__ float red[32];
+    const bf16* xr = x + (size_t)blockIdx.x * in_stride;
+    bf16* yr = y + (size_t)blockIdx.x * out_stride;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s += tof(xr[i]);
+    const float mean = block_sum(s, red) / C;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { const float d = tof(xr[i]) - mean; v += d * d; }
+    const float rstd = rsqrtf(block_sum(v, red) / C + eps);
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+        yr[i] = fromf<bf16>((tof(xr[i]) - mean) * rstd * tof(w[i]) + tof(b[i]));
+}
+
+// row soft-max: fp32 scores [rows, ld_in] (first n valid) -> bf16 probabilities [rows, ld_out], zero padded
+__global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int n, int ld_in, int ld_out) {
+    __shared__ float red[32];
+    const float* sr = s + (size_t)blockIdx.x * ld_in;
+    bf16* pr = p + (size_t)blockIdx.x * ld_out;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(sr[i] - mx);
+    sum = block_sum(sum, red);
+    for (int i = threadIdx.x; i < ld_out; i += blockDim.x)
+        pr[i] = fromf<bf16>(i < n ? expf(sr[i] - mx) / sum : 0.f);
+}
+
+// GroupNorm(32 groups, eps 1e-6, affine) statistics over NHWC bf16: one block per (b, group)
+__global__ void groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats /*[B*G][2]*/, int HW, int C, int G) {
+    __shared__ float red[32];
+    const int b = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+    const bf16* xb = x + (size_t)b * HW * C + g * cg;
+    const long long n = (long long)HW * cg;
+    float s = 0.f, ss = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = tof(xb[(i / cg) * C + (i % cg)]);
+        s += v; ss += v * v;
+    }
+    s = block_sum(s, red); ss = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+        const float mean = s / n;
+        stats[blockIdx.x * 2] = mean;
+        stats[blockIdx.x * 2 + 1] = rsqrtf(fmaxf(ss / n - mean * mean, 0.f) + 1e-6f);
+    }
+}
+// y = GN(x) (*swish): nonlinearity(x) = x*sigmoid(x), vq_model.py:355-357
+__global__ void groupnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const bf16* __restrict__ w,
+                                       const bf16* __restrict__ bsh, bf16* __restrict__ y, long long total, int HW, int C, int G, int swish) {
+    const int cg = C / G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int b = (int)(i / ((long long)HW * C));
+        const float* st = stats + ((size_t)b * G + c / cg) * 2;
+        float v = (tof(x[i]) - st[0]) * st[1] * tof(w[c]) + tof(bsh[c]);
+        if (swish) v = v / (1.0f + expf(-v));
+        y[i] = fromf<bf16>(v);
+    }
+}
+
+// ---- layout / dtype conversions
+template <typename TI>
+__global__ void nchw_to_nhwc_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__ y, int B, int C, int HW, int Cpad) {
+    const long long total = (long long)B * HW * Cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const long long bp = i / Cpad;
+        const int pix = (int)(bp % HW), b = (int)(bp / HW);
+        y[i] = c < C ? fromf<bf16>(tof(x[((size_t)b * C + c) * HW + pix])) : fromf<bf16>(0.f);
+    }
+}
+// conv weight [Cout][Cin][kh][kw] (fp32 or bf16) -> bf16 [Cout][kh][kw][Cin_pad]
+template <typename TI>
+__global__ void conv_weight_pack_kernel(const TI* __restrict__ w, bf16* __restrict__ y, int Cout, int Cin, int KH, int KW, int Cin_pad) {
+    const long long total = (long long)Cout * KH * KW * Cin_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin_pad);
+        long long r = i / Cin_pad;
+        const int kx = (int)(r % KW); r /= KW;
+        const int ky = (int)(r % KH);
+        const int o = (int)(r / KH);
+        y[i] = c < Cin ? fromf<bf16>(tof(w[(((size_t)o * Cin + c) * KH + ky) * KW + kx])) : fromf<bf16>(0.f);
+    }
+}
+template <typename TI>
+__global__ void cast_to_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = fromf<bf16>(tof(x[i]));
+}
+
+// ---- control-map resize to multiples of 14 (dinov2_adapter.py:16-24) fused with the 14x14 patch im2col:
+// out[b*hw + py*w + px][c*196 + ky*14 + kx] (Kpad columns, zero padded) = resized[b][c][py*14+ky][px*14+kx]
+// mode 0: F.interpolate(mode='nearest')  src = floor(dst * in/out)
+// mode 1: bicubic, align_corners=True (A = -0.75), computed in fp32 and rounded to the model dtype like
+//         upsample_bicubic2d on a bf16 tensor (opmath float, output cast)
+__device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+template <typename TI>
+__global__ void resize_patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int h, int w,
+                                       int Kpad, int mode) {
+    const int nh = h * 14, nw = w * 14;
+    const long long total = (long long)B * h * w * Kpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const long long row = i / Kpad;
+        float v = 0.f;
+        if (k < 588) {
+            const int c = k / 196, r = k % 196, ky = r / 14, kx = r % 14;
+            const int px = (int)(row % w), py = (int)((row / w) % h), b = (int)(row / ((long long)w * h));
+            const int oy = py * 14 + ky, ox = px * 14 + kx;
+            const TI* src = img + ((size_t)b * 3 + c) * H * W;
+            if (mode == 0) {
+                const int sy = min((int)floorf(oy * ((float)H / nh)), H - 1);
+                const int sx = min((int)floorf(ox * ((float)W / nw)), W - 1);
+                v = tof(src[(size_t)sy * W + sx]);
+            } else {
+                const float fy = nh > 1 ? oy * ((float)(H - 1) / (nh - 1)) : 0.f;
+                const float fx = nw > 1 ? ox * ((float)(W - 1) / (nw - 1)) : 0.f;
+                const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+                const float ty = fy - iy, tx = fx - ix;
+                const float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+                const float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int yy = min(max(iy - 1 + a, 0), H - 1);
+                    float rowv = 0.f;
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const int xx = min(max(ix - 1 + bb, 0), W - 1);
+                        rowv += tof(src[(size_t)yy * W + xx]) * wx[bb];
+                    }
+                    acc += rowv * wy[a];
+                }
+                v = acc;
+            }
+        }
+        out[i] = fromf<bf16>(v);
+    }
+}
+
+// position embeddings: bicubic (align_corners=False, A=-0.75, fp32) resize of the [G,G,C] grid to [h,w,C], cast to
+// the model dtype (modeling_dinov2.py interpolate_pos_encoding); pos: [1 + G*G, C]
+template <typename TI>
+__global__ void pos_embed_interp_kernel(const TI* __restrict__ pos, bf16* __restrict__ out /*[h*w][C]*/, int G, int h, int w, int C) {
+    const long long total = (long long)h * w * C;
+    const float sy = (float)G / h, sx = (float)G / w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int ox = (int)((i / C) % w), oy = (int)(i / ((long long)C * w));
+        const float fy = (oy + 0.5f) * sy - 0.5f, fx = (ox + 0.5f) * sx - 0.5f;
+        const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+        const float ty = fy - iy, tx = fx - ix;
+        const float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+        const float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(iy - 1 + a, 0), G - 1);
+            float rowv = 0.f;
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const int xx = min(max(ix - 1 + bb, 0), G - 1);
+                rowv += tof(pos[(size_t)(1 + yy * G + xx) * C + c]) * wx[bb];
+            }
+            acc += rowv * wy[a];
+        }
+        out[i] = fromf<bf16>(acc);
+    }
+}
+
+// x[b][0] = cls + pos[0];  x[b][1+i] = patch[b][i] + pos_i   (bf16 adds, modeling_dinov2.py Dinov2Embeddings.forward)
+template <typename TI>
+__global__ void dino_assemble_kernel(const bf16* __restrict__ patch, const TI* __restrict__ cls, const TI* __restrict__ pos0,
+                                     const bf16* __restrict__ pos_i, bf16* __restrict__ x, int B, int hw, int C) {
+    const long long total = (long long)B * (hw + 1) * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int t = (int)((i / C) % (hw + 1)), b = (int)(i / ((long long)C * (hw + 1)));
+        float v;
+        if (t == 0) v = rnd<bf16>(tof(cls[c])) + rnd<bf16>(tof(pos0[c]));
+        else v = tof(patch[((size_t)b * hw + t - 1) * C + c]) + tof(pos_i[(size_t)(t - 1) * C + c]);
+        x[i] = fromf<bf16>(v);
+    }
+}
+
+// ---- VQ codebook: F.normalize(embedding, p=2, dim=-1) (eps 1e-12) in fp32; lookup -> NHWC bf16 padded to Kpad ch
+__global__ void codebook_normalize_kernel(const float* __restrict__ e, float* __restrict__ en, int n, int d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ss = 0.f;
+    for (int k = 0; k < d; ++k) ss += e[(size_t)i * d + k] * e[(size_t)i * d + k];
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    for (int k = 0; k < d; ++k) en[(size_t)i * d + k] = e[(size_t)i * d + k] / nrm;
+}
+__global__ void codebook_lookup_kernel(const float* __restrict__ en, const int* __restrict__ codes, bf16* __restrict__ out,
+                                       long long npix, int d, int Kpad, int n_codes) {
+    const long long total = npix * Kpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const long long pix = i / Kpad;
+        int code = codes[pix];
+        code = min(max(code, 0), n_codes - 1);
+        out[i] = fromf<bf16>(k < d ? en[(size_t)code * d + k] : 0.f);
+    }
+}
+// VectorQuantizer.forward (vq_model.py:216-236): z (fp32 [npix][d]) l2-normalised; d_j = |z|^2 + |e_j|^2 - 2 z.e_j;
+// arg-min over j (lowest index on ties).  One thread per pixel, codebook broadcast through L1.
+__global__ void vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ en, int* __restrict__ idx,
+                                 float* __restrict__ zq /*[npix][d] or null*/, long long npix, int d, int n_codes) {
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    float zz[8];
+    float ss = 0.f;
+    for (int k = 0; k < 8; ++k) { zz[k] = k < d ? z[pix * d + k] : 0.f; ss += zz[k] * zz[k]; }
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    float z2 = 0.f;
+    for (int k = 0; k < 8; ++k) { zz[k] /= nrm; z2 += zz[k] * zz[k]; }
+    float best = INFINITY; int bi = 0;
+    for (int j = 0; j < n_codes; ++j) {
+        float e2 = 0.f, dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float ev = k < d ? __ldg(en + (size_t)j * d + k) : 0.f; e2 += ev * ev; dot += zz[k] * ev; }
+        const float dist = (z2 + e2) - 2.f * dot;
+        if (dist < best) { best = dist; bi = j; }
+    }
+    idx[pix] = bi;
+    if (zq) for (int k = 0; k < d; ++k) zq[pix * d + k] = en[(size_t)bi * d + k];
+}
+// [npix][C] bf16 (NHWC) -> fp32 [npix][d] taking the first d channels
+__global__ void take_channels_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long npix, int C, int d) {
+    const long long total = npix * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        y[i] = tof(x[(i / d) * C + (i % d)]);
+}
+// zq [B*h*w][d] fp32 -> NCHW fp32 [B][d][h][w]
+__global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int HW, int d) {
+    const long long total = (long long)B * HW * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const int k = (int)((i / HW) % d), b = (int)(i / ((long long)HW * d));
+        y[i] = x[((size_t)b * HW + pix) * d + k];
+    }
+}

@@ -144,6 +144,53 @@ int car_op_linear(int32_t dtype, const void* x, const void* w, const void* bias,
 int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void* y, int32_t M, int32_t K, float eps,
                    void* stream);
 
+/* =====================================================================================================
+ * Control encoder: Dinov2_Adapter.forward (autoregressive/models/dinov2_adapter.py:16-29) = resize to multiples
+ * of 14 -> HF Dinov2Model (third-party: transformers, unpinned in requirements.txt:19; 5.5.0 restated) -> drop CLS,
+ * optionally followed by adapter_mlp (generate.py:138).  Arithmetic: bf16 tensor-core operands, fp32 accumulate.
+ * ===================================================================================================== */
+typedef struct CarDino CarDino;
+typedef struct CarDinoDesc {
+    int32_t dtype;            /* dtype of the borrowed weights and of the input image (CAR_BF16 | CAR_F32) */
+    int32_t hidden, heads, layers;
+    int32_t patch;            /* 14 */
+    int32_t pos_grid;         /* 37 (image_size 518 / 14) */
+    int32_t resize_mode;      /* 0 nearest (canny, seg) ; 1 bicubic align_corners=True (others) */
+    int32_t adapter_out_dim;  /* d of adapter_mlp, 0 = no adapter_mlp registered */
+    float   eps;              /* layer_norm_eps 1e-6 */
+} CarDinoDesc;
+typedef struct CarDinoWeights {   /* HF state-dict tensors, in `dtype`; arrays have `layers` entries */
+    const void *cls_token, *pos_emb, *patch_w, *patch_b, *ln_w, *ln_b;
+    const void *const *n1_w, *const *n1_b, *const *q_w, *const *q_b, *const *k_w, *const *k_b, *const *v_w, *const *v_b,
+               *const *o_w, *const *o_b, *const *ls1, *const *n2_w, *const *n2_b, *const *fc1_w, *const *fc1_b,
+               *const *fc2_w, *const *fc2_b, *const *ls2;
+    const void *adapter_fc1, *adapter_fc2;   /* adapter_mlp.fc{1,2}.weight or NULL */
+} CarDinoWeights;
+int car_dino_create(const CarDinoDesc* desc, const CarDinoWeights* w, void* stream, CarDino** out);
+/* image [B,3,H,W] in `dtype`, values in [-1,1]; out bf16 [B, (H/16)(W/16), hidden] or, with apply_mlp, [.., adapter_out_dim] */
+int car_dino_forward(CarDino* m, const void* image, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t apply_mlp,
+                     void* stream);
+int car_dino_destroy(CarDino* m);
+
+/* =====================================================================================================
+ * Image tokenizer: VQModel.decode_code / encode (tokenizer/tokenizer_image/vq_model.py:41-56).
+ * tensors: the fp32 state-dict tensors in canonical order = encoder, decoder, quantize.embedding.weight,
+ * quant_conv, post_quant_conv, each module as (weight, bias) in definition order (controlar_b200/vision.py
+ * `vq_tensor_order`).  Arithmetic: NHWC bf16 activations/weights on tensor cores, fp32 accumulate and statistics.
+ * ===================================================================================================== */
+typedef struct CarVQ CarVQ;
+typedef struct CarVQDesc {
+    int32_t codebook_size, embed_dim, ch, z_channels, n_levels, num_res_blocks;
+    int32_t ch_mult[8];
+} CarVQDesc;
+int car_vq_create(const CarVQDesc* desc, const void* const* tensors, int32_t n_tensors, void* stream, CarVQ** out);
+int car_vq_decode_code(CarVQ* m, const int32_t* codes, int32_t B, int32_t h, int32_t w, float* out_nchw, void* stream);
+/* VQModel.decode (vq_model.py:48-51): quant fp32 [B, e, h, w] */
+int car_vq_decode(CarVQ* m, const float* quant_nchw, int32_t B, int32_t h, int32_t w, float* out_nchw, void* stream);
+int car_vq_encode(CarVQ* m, const float* img_nchw, int32_t B, int32_t H, int32_t W, int32_t* idx_out, float* quant_out,
+                  void* stream);
+int car_vq_destroy(CarVQ* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,22 @@ def test_sampler_oracle_vs_reference():
     q = torch.empty_like(p).exponential_(1)
     torch.manual_seed(5)
     assert torch.equal(torch.multinomial(p, 1), torch.argmax(p / q, -1, keepdim=True))
+
+
+def test_vision_oracles_vs_reference():
+    """DINOv2 adapter + VQ decode/encode restatements against the reference modules' outputs."""
+    from oracle.weights import dinov2_shapes, _fill, make_vq_state_dict
+    from oracle.inputs import control_map
+    from oracle.vision_oracle import dinov2_adapter_oracle, vq_decode_oracle, vq_encode_oracle
+    g = load_golden("dinov2")
+    sd = _fill(dinov2_shapes(384, prefix="model."), g["seed"], 0.02)
+    for ctype in ("canny", "depth"):
+        x = control_map(2, 64, 96, 21, ctype, torch.float32)
+        got = dinov2_adapter_oracle(sd, x, ctype, torch.float32, heads=6)
+        assert rel_l2(got, g[f"small_{ctype}_float32_64x96_out"]) < 1e-4
+    v = load_golden("vq16")
+    vsd = make_vq_state_dict(seed=v["seed"])
+    img = vq_decode_oracle(vsd, v["codes_mr"], [2, 8, 4, 6])
+    assert rel_l2(img, v["image_mr"]) < 1e-4
+    idx, z, _ = vq_encode_oracle(vsd, v["image_mr"].clamp(-1, 1))
+    assert (idx == v["enc_idx_mr"]).float().mean() > 0.99
