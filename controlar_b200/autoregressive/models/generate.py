@@ -51,8 +51,18 @@ def generate(model, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_int
              **sampling_kwargs):
     """Reference generate.py:134-204."""
     if condition is not None:
-        condition = model.adapter(condition)                    # generate.py:137
-        condition = model.adapter_mlp(condition)                # generate.py:138
+        if getattr(model.adapter, "forward", None) is not None and type(model.adapter).__name__ == "Dinov2_Adapter" \
+                and "forward" not in vars(model.adapter) and "forward" not in vars(model.adapter_mlp):
+            # generate.py:137-138 as one library call: DINOv2 forward + adapter_mlp on the dense tensor-core path
+            from ... import vision as _vision
+            enc = getattr(model, "_car_encoder", None)
+            if enc is None or enc.adapter is not model.adapter:
+                enc = _vision.DinoHandle(model.adapter, model.adapter_mlp)
+                object.__setattr__(model, "_car_encoder", enc)
+            condition = enc.forward(condition, apply_mlp=True)
+        else:
+            condition = model.adapter(condition)                # generate.py:137
+            condition = model.adapter_mlp(condition)            # generate.py:138
     use_cfg = cfg_scale > 1.0
     if model.model_type == "c2i":
         cond_combined = torch.cat([cond, torch.ones_like(cond) * model.num_classes]) if use_cfg else cond
