@@ -98,4 +98,22 @@ def cur_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None passes through)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("controlar_b200: tensor is not on a CUDA device (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("controlar_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _ptr_array(ts):
+    arr = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = _ptr(t)
+    return arr
+
+
 from . import vision as _vision  # noqa: E402,F401  (registers the car_dino_* / car_vq_* prototypes in PROTOTYPES)

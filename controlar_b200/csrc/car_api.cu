@@ -10,19 +10,21 @@
 #include "attention.cuh"
 #include "sampler.cuh"
 #include "misc.cuh"
+#include "decode_persistent.cuh"
+#include <algorithm>
 
 thread_local std::string g_car_err;
 std::atomic<long long> g_car_launches{0};
 
 // development knobs (environment, read once): CAR_PDL, CAR_L2PF, CAR_NSPLIT, CAR_NB_QKV/WO/W13/W2/HEAD
-struct Tune { int pdl, l2pf, nsplit, nb[5], skip, empty, dbg; };
+struct Tune { int pdl, l2pf, nsplit, nb[5], skip, empty, dbg, mega, mega_pf; };
 static long long* g_dbg = nullptr;   // [5 kernels][8] clock stamps (CAR_DBG=1)
 __global__ void empty_kernel(int) {}
 static const Tune& tune() {
     static Tune t = [] {
         Tune x;
         auto gi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
-        x.dbg = gi("CAR_DBG", 0); x.skip = gi("CAR_SKIP", 0); x.empty = gi("CAR_EMPTY", 0);
+        x.mega = gi("CAR_MEGA", 1); x.mega_pf = gi("CAR_MEGA_PF", 1); x.dbg = gi("CAR_DBG", 0); x.skip = gi("CAR_SKIP", 0); x.empty = gi("CAR_EMPTY", 0);
         x.pdl = gi("CAR_PDL", 1); x.l2pf = gi("CAR_L2PF", 1); x.nsplit = gi("CAR_NSPLIT", 0);
         x.nb[EPI_STORE] = 0; x.nb[EPI_QKV] = gi("CAR_NB_QKV", 0); x.nb[EPI_RESID] = gi("CAR_NB_RESID", 0);
         x.nb[EPI_SWIGLU] = gi("CAR_NB_W13", 0); x.nb[EPI_LOGITS] = gi("CAR_NB_HEAD", 0);
@@ -72,6 +74,13 @@ struct CarState {
     bool graph_ok;
     CarSampling gsp;
     const float* gnoise;
+    // persistent decode kernel (decode_persistent.cuh)
+    void** pk_ptrs;          // device arrays of per-layer pointers [8][L]
+    int* pk_part;            // [4][grid + 1] block offsets per CTA
+    uint2 *pk_h2[2], *pk_h1[2], *pk_att[2], *pk_act[2], *pk_qkv[2], *pk_partial[2];
+    int pk_part_slots, pk_grid; bool pk_ok;
+    unsigned int* pk_bar; unsigned int pk_bar_count, pk_tag_base;
+    size_t pk_pkt_bytes; void* pk_pkt_base;
     std::vector<void*> owned;
 };
 
@@ -252,6 +261,72 @@ extern "C" int car_model_destroy(CarModel* m) {
 // ---------------------------------------------------------------------------------------------------------
 // state
 // ---------------------------------------------------------------------------------------------------------
+// block ownership of the persistent decode kernel: counts per CTA balanced on streamed bytes per token
+static void pk_partition(const CarModelDesc& d, int G, std::vector<int>& table) {
+    const int nQ = 3 * d.dim / 8, nD = d.dim / 8, nP = d.ffn_dim / 8, nH = d.vocab_size / 8;
+    const double L = d.n_layer;
+    const double wQ = L * 16.0 * d.dim, wD = L * 16.0 * (d.dim + d.ffn_dim), wP = L * 32.0 * d.dim, wH = 16.0 * d.dim;
+    std::vector<double> load(G, 0.0);
+    std::vector<int> cQ(G, 0), cD(G, 0), cP(G, 0), cH(G, 0);
+    for (int i = 0; i < nD; ++i) { cD[i % G] += 1; load[i % G] += wD; }
+    auto spread = [&](int n, double w, std::vector<int>& cnt) {
+        for (int i = 0; i < n; ++i) {
+            int best = 0;
+            for (int c = 1; c < G; ++c) if (load[c] < load[best] - 1e-9) best = c;
+            cnt[best] += 1; load[best] += w;
+        }
+    };
+    spread(nP, wP, cP); spread(nQ, wQ, cQ);
+    (void)wH;
+    for (int i = 0; i < nH; ++i) cH[i % G] += 1;      // the head ends in a grid barrier: its latency, not its bytes, is what counts
+    table.assign(4 * (G + 1), 0);
+    const std::vector<int>* cs[4] = {&cQ, &cD, &cP, &cH};
+    for (int k = 0; k < 4; ++k)
+        for (int c = 0; c < G; ++c) table[k * (G + 1) + c + 1] = table[k * (G + 1) + c] + (*cs[k])[c];
+}
+
+static int pk_state_setup(CarState* s) {
+    const CarModelDesc& d = s->m->d;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int G = sms, L = d.n_layer;
+    s->pk_grid = G;
+    const int nbh = s->b_eff * d.n_head;
+    // shapes the kernel is instantiated for (else car_generate falls back to the per-kernel graph chain)
+    s->pk_ok = s->b_eff <= 16 && d.dim % 32 == 0 && d.dim <= 16 * 3 * 32 && d.ffn_dim % 32 == 0 && d.ffn_dim <= 16 * 7 * 32 &&
+               d.dim / 8 <= 2 * G && d.vocab_size <= 16384 && d.ffn_dim % 8 == 0 && nbh <= 5 * G &&
+               2 * ((d.ffn_dim / 32 + PK_UNIT_KS - 1) / PK_UNIT_KS) <= PK_NSLOT;
+    if (!s->pk_ok) return CAR_OK;
+    std::vector<const void*> hp(8 * L);
+    for (int l = 0; l < L; ++l) {
+        hp[0 * L + l] = s->m->g_wqkv[l]; hp[1 * L + l] = s->m->g_wo[l]; hp[2 * L + l] = s->m->g_w13[l]; hp[3 * L + l] = s->m->g_w2[l];
+        hp[4 * L + l] = s->m->attention_norm[l]; hp[5 * L + l] = s->m->ffn_norm[l]; hp[6 * L + l] = s->kc[l]; hp[7 * L + l] = s->vc[l];
+    }
+    std::vector<int> table;
+    pk_partition(d, G, table);
+    s->pk_part_slots = G / std::max(1, nbh) + 3;
+    // packet buffers: two parities of H2, H1, ATT (K = dim), ACT (K = ffn), QKV, PARTIAL; one allocation, zeroed (tag 0 = never)
+    const size_t a_d = (size_t)(d.dim / 32) * 2048, a_f = (size_t)(d.ffn_dim / 32) * 2048;
+    const size_t qkv_b = (size_t)3 * 16 * d.n_head * 8 * 4 * 8, part_b = (size_t)nbh * s->pk_part_slots * 66 * 8;
+    const size_t total = 2 * (3 * a_d + a_f + qkv_b + part_b);
+    CAR_TRY(alloc_dev(s->owned, (void**)&s->pk_ptrs, hp.size() * sizeof(void*)));
+    CAR_TRY(alloc_dev(s->owned, (void**)&s->pk_part, table.size() * sizeof(int)));
+    CAR_TRY(alloc_dev(s->owned, (void**)&s->pk_bar, 64));
+    CAR_TRY(alloc_dev(s->owned, &s->pk_pkt_base, total));
+    s->pk_pkt_bytes = total;
+    unsigned char* q = (unsigned char*)s->pk_pkt_base;
+    for (int par = 0; par < 2; ++par) {
+        s->pk_h2[par] = (uint2*)q; q += a_d; s->pk_h1[par] = (uint2*)q; q += a_d; s->pk_att[par] = (uint2*)q; q += a_d;
+        s->pk_act[par] = (uint2*)q; q += a_f; s->pk_qkv[par] = (uint2*)q; q += qkv_b; s->pk_partial[par] = (uint2*)q; q += part_b;
+    }
+    CAR_CUDA(cudaMemcpy(s->pk_ptrs, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    CAR_CUDA(cudaMemcpy(s->pk_part, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CAR_CUDA(cudaMemset(s->pk_bar, 0, 64));
+    CAR_CUDA(cudaMemset(s->pk_pkt_base, 0, total));
+    return CAR_OK;
+}
+
 extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N, void* const* k_cache, void* const* v_cache,
                                 const float* rope_table, CarState** out) {
     if (!m || !k_cache || !v_cache || !rope_table || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
@@ -285,6 +360,13 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     if (r == CAR_OK && cudaMemset(s->pos, 0, 16) != cudaSuccess) r = CAR_ERR_CUDA;
     if (r != CAR_OK) { for (void* p : s->owned) cudaFree(p); delete s; return r; }
     s->done_ctr = s->pos + 1;
+    // persistent decode kernel resources (bf16 only)
+    s->pk_ptrs = nullptr; s->pk_part = nullptr; s->pk_bar = nullptr; s->pk_grid = 0; s->pk_ok = false;
+    s->pk_bar_count = 0; s->pk_tag_base = 0; s->pk_pkt_base = nullptr; s->pk_pkt_bytes = 0;
+    if (d.dtype == CAR_BF16) {
+        int r2 = pk_state_setup(s);
+        if (r2 != CAR_OK) { for (void* p : s->owned) cudaFree(p); delete s; return r2; }
+    }
     s->emb_mask_store = s->emb_mask;
     s->emb_mask = nullptr;                           // all-ones until car_state_set_emb_mask
     s->gsp = CarSampling{};
@@ -506,9 +588,8 @@ static int launch_sampler(const SampleArgs& a, cudaStream_t st) {
         CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    const size_t smem = (size_t)a.V * 4;
-    if (smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "vocab too large for the sampler's shared-memory row");
-    CAR_LAUNCH(sample_kernel, a.B, SMP_THREADS, smem, st, a);
+    if (a.V > SMP_THREADS * SMP_EPT) CAR_FAIL(CAR_ERR_UNSUPPORTED, "vocab larger than 16384 is not supported by the fused sampler");
+    CAR_LAUNCH(sample_kernel, a.B, SMP_THREADS, 0, st, a);
     return CAR_OK;
 }
 
@@ -537,6 +618,83 @@ static int loop_sample_args(CarState* s, const CarSampling* sp, const float* noi
     return CAR_OK;
 }
 
+// the whole decode loop as one persistent cooperative kernel (decode_persistent.cuh)
+static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st) {
+    const CarModelDesc& d = s->m->d;
+    const int L = d.n_layer;
+    if (s->pk_tag_base > 0x7fff0000u) {   // tag wrap: restart the epoch counter on zeroed packets
+        CAR_CUDA(cudaMemsetAsync(s->pk_pkt_base, 0, s->pk_pkt_bytes, st));
+        s->pk_tag_base = 0;
+    }
+    PkParams P;
+    memset(&P, 0, sizeof(P));
+    P.dim = d.dim; P.F = d.ffn_dim; P.V = d.vocab_size; P.L = L; P.H = d.n_head; P.T = s->T; P.S = s->S; P.n_img = s->N;
+    P.b_eff = s->b_eff; P.B = a.B; P.eps = d.norm_eps; P.cs = s->cs;
+    P.tok_emb = (const bf16*)s->m->tok_emb; P.norm_w = (const bf16*)s->m->norm; P.w_out = (const uint4*)s->m->g_output;
+    void** pp = s->pk_ptrs;
+    P.wqkv = (const uint4* const*)(pp + 0 * L); P.wo = (const uint4* const*)(pp + 1 * L); P.w13 = (const uint4* const*)(pp + 2 * L);
+    P.w2 = (const uint4* const*)(pp + 3 * L); P.attn_norm = (const bf16* const*)(pp + 4 * L); P.ffn_norm = (const bf16* const*)(pp + 5 * L);
+    P.kc = (bf16* const*)(pp + 6 * L); P.vc = (bf16* const*)(pp + 7 * L);
+    for (int j = 0; j < 3; ++j) P.ctrl[j] = (const bf16*)s->ctrl[j];
+    P.has_ctrl = s->has_ctrl ? 1 : 0;
+    P.rope = s->rope; P.emb_mask = s->emb_mask; P.logits = s->logits; P.part = s->pk_part;
+    for (int par = 0; par < 2; ++par) {
+        P.h2[par] = s->pk_h2[par]; P.h1[par] = s->pk_h1[par]; P.att[par] = s->pk_att[par]; P.act[par] = s->pk_act[par];
+        P.qkv[par] = s->pk_qkv[par]; P.partial[par] = s->pk_partial[par];
+    }
+    P.part_slots = s->pk_part_slots; P.tag_base = s->pk_tag_base; P.bar = s->pk_bar; P.bar_base = s->pk_bar_count;
+    P.smp = a; P.n_steps = n_tokens;
+    { const char* e = getenv("CAR_EXP"); P.exp_flags = e ? atoi(e) : 0; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(pk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_TOTAL));
+        attr_set = true;
+    }
+    int occ = 0;
+    CAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_decode_kernel, PK_THREADS, PK_SMEM_TOTAL));
+    if (occ < 1) CAR_FAIL(CAR_ERR_UNSUPPORTED, "persistent decode kernel does not fit on an SM");
+    static long long* mdbg = nullptr;
+    const size_t dbg_n = (size_t)s->pk_grid * 64;
+    if (tune().dbg) {
+        if (!mdbg) { cudaMalloc(&mdbg, dbg_n * 8); }
+        cudaMemsetAsync(mdbg, 0, dbg_n * 8, st);
+        P.dbg = mdbg; P.dbg_step = std::max(0, std::min(n_tokens - 2, tune().dbg));
+    }
+    void* args[] = {&P};
+    CAR_CUDA(cudaLaunchCooperativeKernel((const void*)pk_decode_kernel, dim3(s->pk_grid), dim3(PK_THREADS), args, PK_SMEM_TOTAL, st));
+    s->pk_bar_count += (unsigned int)(n_tokens - 1) * (unsigned int)s->pk_grid;        // one grid barrier per decoded token
+    s->pk_tag_base += (unsigned int)(n_tokens - 1) * (unsigned int)(L + 1);
+    g_car_launches.fetch_add(1, std::memory_order_relaxed);
+    if (tune().dbg) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> t(dbg_n);
+        cudaMemcpy(t.data(), mdbg, dbg_n * 8, cudaMemcpyDeviceToHost);
+        const int G = s->pk_grid;
+        long long t0 = t[0];
+        for (int c = 0; c < G; ++c) if (t[(size_t)c * 64]) t0 = std::min(t0, t[(size_t)c * 64]);
+        auto stat = [&](int slot, const char* name) {
+            std::vector<long long> v;
+            for (int c = 0; c < G; ++c) if (t[(size_t)c * 64 + slot]) v.push_back(t[(size_t)c * 64 + slot] - t0);
+            if (v.empty()) return;
+            std::sort(v.begin(), v.end());
+            int amax = 0;
+            for (int c = 0; c < G; ++c) if (t[(size_t)c * 64 + slot] - t0 == v.back()) amax = c;
+            fprintf(stderr, "[pk] %-22s n=%3zu  min %8.2f  med %8.2f  max %8.2f us (CTA %d)\n", name, v.size(), v.front() * 1e-3, v[v.size() / 2] * 1e-3,
+                    v.back() * 1e-3, amax);
+        };
+        fprintf(stderr, "[pk] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
+        stat(0, "step start"); stat(1, "sampler done");
+        const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
+        for (int k = 0; k < 5; ++k) {
+            char buf[64];
+            const char* sub[5] = {"start", k == 1 ? "q polled" : "A polled", k == 1 ? "keys done" : "weights+norm", k == 1 ? "end" : "mma done", "end"};
+            for (int j = 0; j < (k == 1 ? 4 : 5); ++j) { snprintf(buf, sizeof buf, "L3 %s %s", nm[k], sub[j]); stat(8 + 8 * k + j, buf); }
+        }
+        stat(3, "head done"); stat(4, "barrier passed");
+    }
+    return CAR_OK;
+}
+
 extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise, int32_t* tokens_out,
                             void* stream) {
     if (!s || !sp || !tokens_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
@@ -545,6 +703,14 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
     cudaStream_t st = (cudaStream_t)stream;
     SampleArgs a;
     CAR_TRY(loop_sample_args(s, sp, noise, a));
+    if (s->m->d.dtype == CAR_BF16 && tune().mega && s->pk_ok) {
+        CAR_TRY(launch_pk(s, a, n_tokens, st));
+        CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, a.B,
+                                   cudaMemcpyDeviceToDevice, st));
+        CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1 + n_tokens);
+        s->prefilled = false;
+        return CAR_OK;
+    }
     // token 0 from the prefill logits (generate.py:198); its fused tail writes h for position T and bumps pos
     CAR_TRY(launch_sampler(a, st));
     if (n_tokens > 1) {

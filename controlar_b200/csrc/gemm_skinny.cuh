@@ -22,8 +22,10 @@ struct EpiParams {
     int M;                // valid rows
     int rpb;              // rows per batch element: T in prefill, 1 in decode
     const int* pos_ptr;   // decode: device scalar with the sequence position; null => pos = row % rpb
+    int pos_fixed_p1;     // persistent decode kernel: position + 1 passed by value (0 = unused)
     // EPI_STORE
     void* out; int ldo; int act; const void* bias;
+    int out_reps; long long out_rep_stride;   // EPI_SWIGLU: extra replicas of the output (persistent kernel)
     // EPI_RESID (+ optional control add for the *next* layer group)
     void* h; int ldh;
     const void* ctrl; int n_img; int T; float cs;
@@ -50,14 +52,16 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& ep, const float* t
             const float u = rnd<T>(tile[m * ldt + jj * 16 + 8 + ci]);
             const float s = rnd<T>(silu_f(g));
             const int col = ((nb0 >> 1) + jj) * 8 + ci;
-            ((T*)ep.out)[(size_t)r * ep.ldo + col] = fromf<T>(s * u);
+            const T ov = fromf<T>(s * u);
+            ((T*)ep.out)[(size_t)r * ep.ldo + col] = ov;
+            for (int rep = 1; rep < ep.out_reps; ++rep) ((T*)ep.out)[(size_t)rep * ep.out_rep_stride + (size_t)r * ep.ldo + col] = ov;
             continue;
         }
         const int c = cp * 2;
         const int n = nb0 * 8 + c;
         float v0 = tile[m * ldt + c], v1 = tile[m * ldt + c + 1];
         const int b = r / ep.rpb;
-        const int pos = ep.pos_ptr ? ld_cg(ep.pos_ptr) : (r - b * ep.rpb);
+        const int pos = ep.pos_fixed_p1 ? ep.pos_fixed_p1 - 1 : (ep.pos_ptr ? ld_cg(ep.pos_ptr) : (r - b * ep.rpb));
         switch (ep.kind) {
             case EPI_STORE: {
                 if (ep.bias) { v0 += tof(((const T*)ep.bias)[n]); v1 += tof(((const T*)ep.bias)[n + 1]); }

@@ -31,6 +31,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+__device__ __forceinline__ float exp1_from_bits(uint32_t x);
+// Exp(1) draw of element i of row b at token `step` (kept out of line: it sits in a fully unrolled loop)
+__device__ __noinline__ float exp1_noise(uint32_t seed_lo, uint32_t seed_hi, int i, int b, int step) {
+    uint32_t r[4];
+    philox4x32_10(seed_lo, seed_hi, (uint32_t)(i >> 2), (uint32_t)b, (uint32_t)step, 0x43415231u, r);
+    return exp1_from_bits(r[i & 3]);
+}
 __device__ __forceinline__ float exp1_from_bits(uint32_t x) {
     // u in (0,1]: (x + 1) * 2^-32 ;  q = -log(u) ~ Exp(1)
     const float u = ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
@@ -54,163 +61,175 @@ struct SampleArgs {
     int* tok_buf;           // [b_eff] int32 tokens consumed by teacher-free decode
     int* pos_ptr;           // device scalar: position of the token being produced is *pos_ptr + 1
     int* done_ctr;          // ticket: the last block to finish advances *pos_ptr
+    int pos_val;            // position when pos_ptr is null (persistent decode kernel)
+    float* ssq_rows;        // optional [16]: sum of squares of the written h rows (index = row), else null
+    int h_reps; long long h_rep_stride;   // extra replicas of h_out (persistent kernel), 0/1 = none
 };
 
 template <typename T>
-__device__ __forceinline__ void write_next_h(const SampleArgs& a, int b_row, int tok, int pos_next) {
+__device__ __forceinline__ void write_next_h(const SampleArgs& a, int b_row, int tok, int pos_next, float* red32) {
     // h = tok_embeddings[tok] (+ cs * ctrl0[b][pos_next - T + 1])    gpt_t2i.py:445,466
     const T* e = (const T*)a.tok_emb + (size_t)tok * a.d;
     T* h = (T*)a.h_out + (size_t)b_row * a.d;
     const int p = pos_next - a.T + 1;
     const T* c = (a.ctrl0 && p >= 0 && p < a.n_img) ? (const T*)a.ctrl0 + ((size_t)b_row * a.n_img + p) * a.d : nullptr;
+    float ss = 0.f;
     for (int k = threadIdx.x; k < a.d; k += blockDim.x) {
         float v = tof(e[k]);
         if (c) v = rnd<T>(v + rnd<T>(a.cs * tof(c[k])));
-        h[k] = fromf<T>(v);
+        const T hv = fromf<T>(v);
+        h[k] = hv;
+        for (int rep = 1; rep < a.h_reps; ++rep) h[(size_t)rep * a.h_rep_stride + k] = hv;
+        ss += v * v;
+    }
+    if (a.ssq_rows) {     // deterministic block reduction (fixed thread->element map, fixed tree)
+        ss = warp_sum(ss);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red32[w];
+            a.ssq_rows[b_row] = t;
+        }
     }
 }
 
-// one CTA per image
-__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
-    extern __shared__ float z[];                  // [V]
-    __shared__ unsigned int hist[256];
-    __shared__ float red_f[32];
-    __shared__ int red_i[32];
-    __shared__ unsigned int sel_prefix, sel_k;
-    __shared__ float s_thr;
-    __shared__ int s_tok;
+// Block-wide deterministic reductions (fixed tree): `red` holds THREADS/32 slots.
+template <int THREADS> __device__ __forceinline__ float smp_block_sum(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += red[w];
+    return s;
+}
+template <int THREADS> __device__ __forceinline__ float smp_block_max(float v, float* red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = red[0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) s = fmaxf(s, red[w]);
+    return s;
+}
+template <int THREADS> __device__ __forceinline__ unsigned smp_block_count(unsigned v, unsigned* red) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned s = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += red[w];
+    return s;
+}
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One CTA per image (b).  The row lives in registers: thread t owns elements t, t+THREADS, ... (EPT of them).
+//   top-k : exact k-th largest by a 32-step bit-wise bisection on the order-preserving integer key (count >= candidate)
+//   soft-max / nucleus / race only touch the kept elements (k of V), Philox is evaluated per kept element.
+template <int THREADS, int EPT>
+__device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
+    __shared__ float red_f[THREADS / 32];
+    __shared__ unsigned red_u[THREADS / 32];
+    __shared__ int red_i[THREADS / 32];
+    __shared__ int s_tok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = a.V;
-    const int pos = a.pos_ptr ? ld_cg(a.pos_ptr) : 0;
+    const int pos = a.pos_ptr ? ld_cg(a.pos_ptr) : a.pos_val;
     const int step = a.pos_ptr ? (pos - a.T + 1) : a.step;   // index of the token being produced
     bool cfg_on = a.cfg_on != 0;
     if (a.cfg_interval > -1 && step - 1 > a.cfg_interval) cfg_on = false;
 
-    // ---- CFG combine + temperature
+    // ---- CFG combine + temperature (generate.py:103-107, :60)
+    float zr[EPT];
     const float* lc = a.logits + (size_t)b * V;
     const float* lu = a.logits + (size_t)(b + a.B) * V;
-    for (int i = tid; i < V; i += SMP_THREADS) {
-        float v = __ldcg(lc + i);
-        if (a.use_cfg && cfg_on) { const float u = __ldcg(lu + i); v = u + (v - u) * a.cfg_scale; }
-        z[i] = v * a.inv_temp;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int i = tid + j * THREADS;
+        float v = -INFINITY;
+        if (i < V) {
+            v = __ldcg(lc + i);
+            if (a.use_cfg && cfg_on) { const float u = __ldcg(lu + i); v = u + (v - u) * a.cfg_scale; }
+            v *= a.inv_temp;
+        }
+        zr[j] = v;
     }
-    __syncthreads();
-
-    // ---- top-k: k-th largest by 4x8-bit radix select; keep z >= thr (ties kept, generate.py:37)
+    // ---- top-k threshold (ties at the threshold are kept, generate.py:37).  The row is turned into its order-preserving
+    // integer keys in place (the map is a bijection), bisected, and turned back — one register array, not two.
     if (a.top_k > 0 && a.top_k < V) {
-        if (tid == 0) { sel_prefix = 0; sel_k = (unsigned)a.top_k; }
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            for (int i = tid; i < 256; i += SMP_THREADS) hist[i] = 0;
-            __syncthreads();
-            const unsigned prefix = sel_prefix;
-            const unsigned pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-            for (int i = tid; i < V; i += SMP_THREADS) {
-                const unsigned key = float_order_key(z[i]);
-                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned k = sel_k, bin = 255;
-                for (;; --bin) {
-                    if (hist[bin] >= k) break;
-                    k -= hist[bin];
-                    if (bin == 0) break;
-                }
-                sel_k = k;
-                sel_prefix = prefix | (bin << shift);
-            }
-            __syncthreads();
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) zr[j] = __uint_as_float((tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u);
+        unsigned cand = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned tryv = cand | (1u << bit);
+            unsigned c = 0;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) c += __float_as_uint(zr[j]) >= tryv ? 1u : 0u;
+            if (smp_block_count<THREADS>(c, red_u) >= (unsigned)a.top_k) cand = tryv;
         }
-        if (tid == 0) {
-            const unsigned key = sel_prefix;
-            const unsigned u = (key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key;
-            s_thr = __uint_as_float(u);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const unsigned key = __float_as_uint(zr[j]);
+            zr[j] = key < cand ? -INFINITY : __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
         }
-        __syncthreads();
-        const float thr = s_thr;
-        for (int i = tid; i < V; i += SMP_THREADS) if (z[i] < thr) z[i] = -INFINITY;
-        __syncthreads();
     }
-
-    // ---- soft-max (max, sum of exp)
+    // ---- soft-max over the kept elements
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += SMP_THREADS) mx = fmaxf(mx, z[i]);
-    mx = warp_max(mx);
-    if (lane == 0) red_f[warp] = mx;
-    __syncthreads();
-    mx = red_f[0];
-    for (int w = 1; w < SMP_THREADS / 32; ++w) mx = fmaxf(mx, red_f[w]);
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) mx = fmaxf(mx, zr[j]);
+    mx = smp_block_max<THREADS>(mx, red_f);
     float sum = 0.f;
-    for (int i = tid; i < V; i += SMP_THREADS) { const float e = expf(z[i] - mx); z[i] = e; sum += e; }
-    sum = warp_sum(sum);
-    if (lane == 0) red_f[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-    for (int w = 0; w < SMP_THREADS / 32; ++w) sum += red_f[w];
-    __syncthreads();
-
-    // ---- nucleus (top-p), generate.py:40-55: in descending order a token is removed iff the cumulative
-    // probability of the tokens strictly before it exceeds top_p (first always kept).  Equivalently token x is
-    // kept iff f(p_x) <= top_p with f(v) = mass of tokens with probability > v; f is a non-increasing step
-    // function, so the kept set is {p >= tau*}; tau* is bracketed by 30 bisection steps (tokens within 2^-30 of
-    // the boundary count as ties and are kept; torch.sort's order among exact ties is unspecified anyway).
-    float keep_above = -1.f;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const float e = zr[j] == -INFINITY ? 0.f : expf(zr[j] - mx);
+        zr[j] = e;
+        sum += e;
+    }
+    sum = smp_block_sum<THREADS>(sum, red_f);
+    // ---- nucleus (top-p), generate.py:40-55: in descending order a token is removed iff the cumulative probability
+    // of the tokens strictly before it exceeds top_p (first always kept).  Equivalently token x is kept iff
+    // f(p_x) <= top_p with f(v) = mass of tokens with probability > v; f is a non-increasing step function, so the
+    // kept set is {p >= tau*}; tau* is bracketed by 30 bisection steps (tokens within 2^-30 of the boundary count as
+    // ties and are kept; torch.sort's order among exact ties is unspecified anyway).
     if (a.top_p < 1.0f) {
         float lo = 0.f, hi = 1.0f;                       // f(lo) > top_p >= f(hi)
         for (int it = 0; it < 30; ++it) {
             const float mid = 0.5f * (lo + hi);
             float ma = 0.f;
-            for (int i = tid; i < V; i += SMP_THREADS) { const float p = z[i] / sum; if (p > mid) ma += p; }
-            ma = warp_sum(ma);
-            if (lane == 0) red_f[warp] = ma;
-            __syncthreads();
-            ma = 0.f;
-            for (int w = 0; w < SMP_THREADS / 32; ++w) ma += red_f[w];
-            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) { const float p = zr[j] / sum; if (p > mid) ma += p; }
+            ma = smp_block_sum<THREADS>(ma, red_f);
             if (ma <= a.top_p) hi = mid; else lo = mid;
         }
-        keep_above = lo;
         float s2 = 0.f;
-        for (int i = tid; i < V; i += SMP_THREADS) {
-            if (!(z[i] / sum > keep_above)) z[i] = 0.f;
-            s2 += z[i];
-        }
-        s2 = warp_sum(s2);
-        if (lane == 0) red_f[warp] = s2;
-        __syncthreads();
-        s2 = 0.f;
-        for (int w = 0; w < SMP_THREADS / 32; ++w) s2 += red_f[w];
-        __syncthreads();
-        sum = s2;                                        // soft-max over the kept logits only
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) { if (!(zr[j] / sum > lo)) zr[j] = 0.f; s2 += zr[j]; }
+        sum = smp_block_sum<THREADS>(s2, red_f);         // soft-max over the kept logits only
     }
-    for (int i = tid; i < V; i += SMP_THREADS) z[i] = z[i] / sum;
-    __syncthreads();
-    if (a.probs_out) for (int i = tid; i < V; i += SMP_THREADS) a.probs_out[(size_t)b * V + i] = z[i];
-
+    if (a.probs_out) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) { const int i = tid + j * THREADS; if (i < V) a.probs_out[(size_t)b * V + i] = zr[j] / sum; }
+    }
     // ---- draw: arg-max of p (greedy) or of p / q (exponential race); lowest index wins ties
     float best = -1.f; int besti = 0x7fffffff;
     const float* nz = a.noise ? a.noise + ((size_t)(a.noise_per_step ? step : 0) * a.B + b) * V : nullptr;
-    if (a.sample_logits && a.noise == nullptr) {
-        for (int i4 = tid; i4 < (V + 3) / 4; i4 += SMP_THREADS) {
-            uint32_t r[4];
-            philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)i4, (uint32_t)b, (uint32_t)step, 0x43415231u, r);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i4 * 4 + j;
-                if (i < V) {
-                    const float s = z[i] / exp1_from_bits(r[j]);
-                    if (s > best) { best = s; besti = i; }
-                }
+    for (int j = 0; j < EPT; ++j) {
+        const int i = tid + j * THREADS;
+        if (i < V && zr[j] > 0.f) {
+            float s = zr[j] / sum;
+            if (a.sample_logits) {
+                float q;
+                if (nz) q = nz[i];
+                else q = exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
+                s = s / q;
             }
-        }
-    } else {
-        for (int i = tid; i < V; i += SMP_THREADS) {
-            float s = z[i];
-            if (a.sample_logits) s = s / nz[i];
-            if (s > best) { best = s; besti = i; }
+            if (s > best || (s == best && i < besti)) { best = s; besti = i; }
         }
     }
 #pragma unroll
@@ -219,11 +238,12 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
         if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
+    __syncthreads();
     if (lane == 0) { red_f[warp] = best; red_i[warp] = besti; }
     __syncthreads();
     if (tid == 0) {
         float bb = red_f[0]; int bi = red_i[0];
-        for (int w = 1; w < SMP_THREADS / 32; ++w)
+        for (int w = 1; w < THREADS / 32; ++w)
             if (red_f[w] > bb || (red_f[w] == bb && red_i[w] < bi)) { bb = red_f[w]; bi = red_i[w]; }
         s_tok = bi;
         if (a.tokens_ld > 0) a.idx_out[(size_t)b * a.tokens_ld + step] = bi;
@@ -236,23 +256,26 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
     if (a.h_out) {
         const int tok = s_tok;
         if (a.dtype == CAR_BF16) {
-            write_next_h<bf16>(a, b, tok, pos + 1);
-            if (a.use_cfg) write_next_h<bf16>(a, b + a.B, tok, pos + 1);
+            write_next_h<bf16>(a, b, tok, pos + 1, red_f);
+            if (a.use_cfg) write_next_h<bf16>(a, b + a.B, tok, pos + 1, red_f);
         } else {
-            write_next_h<float>(a, b, tok, pos + 1);
-            if (a.use_cfg) write_next_h<float>(a, b + a.B, tok, pos + 1);
+            write_next_h<float>(a, b, tok, pos + 1, red_f);
+            if (a.use_cfg) write_next_h<float>(a, b + a.B, tok, pos + 1, red_f);
         }
     }
-    // ---- the last block to finish advances the device-side position / step counters
+    // ---- the last block to finish advances the device-side position
     if (a.done_ctr) {
         __syncthreads();
         if (tid == 0) {
             __threadfence();
             const int old = atomicAdd(a.done_ctr, 1);
-            if (old == (int)gridDim.x - 1) {
+            if (old == a.B - 1) {
                 *a.done_ctr = 0;
                 if (a.pos_ptr) *a.pos_ptr = pos + 1;
             }
         }
     }
 }
+
+constexpr int SMP_EPT = 16;                       // V <= SMP_THREADS * SMP_EPT = 16384
+__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) { sample_body<SMP_THREADS, SMP_EPT>(a, blockIdx.x); }

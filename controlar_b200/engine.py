@@ -10,24 +10,7 @@ from typing import List, Optional
 import torch
 
 from . import _lib
-from ._lib import CarModelDesc, CarSampling, CarWeights, check, cur_stream, dtype_code
-
-
-def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
-    if t is None:
-        return None
-    if not t.is_cuda:
-        raise RuntimeError("controlar_b200: tensor is not on a CUDA device (there is no CPU fallback)")
-    if not t.is_contiguous():
-        raise RuntimeError("controlar_b200: tensor must be contiguous")
-    return t.data_ptr()
-
-
-def _ptr_array(ts: List[torch.Tensor]):
-    arr = (C.c_void_p * len(ts))()
-    for i, t in enumerate(ts):
-        arr[i] = _ptr(t)
-    return arr
+from ._lib import CarModelDesc, CarSampling, CarWeights, check, cur_stream, dtype_code, _ptr, _ptr_array
 
 
 class ARModelHandle:

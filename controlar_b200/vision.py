@@ -7,8 +7,7 @@ from typing import List
 import torch
 
 from . import _lib
-from ._lib import check, cur_stream, dtype_code
-from .engine import _ptr, _ptr_array
+from ._lib import check, cur_stream, dtype_code, _ptr, _ptr_array
 
 
 class CarDinoDesc(C.Structure):
