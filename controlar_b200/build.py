@@ -28,7 +28,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("CAR_PK_TRACE"):        # dev: per-phase globaltimer stamps in the persistent decode kernel (CAR_DBG=<step>)
+        flags.append("-DPK_TRACE")
+    cmd = [nvcc] + flags + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

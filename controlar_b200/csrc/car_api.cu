@@ -654,7 +654,7 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
     CAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_decode_kernel, PK_THREADS, PK_SMEM_TOTAL));
     if (occ < 1) CAR_FAIL(CAR_ERR_UNSUPPORTED, "persistent decode kernel does not fit on an SM");
     static long long* mdbg = nullptr;
-    const size_t dbg_n = (size_t)s->pk_grid * 64;
+    const size_t dbg_n = (size_t)s->pk_grid * 64 + 5 * 256;
     if (tune().dbg) {
         if (!mdbg) { cudaMalloc(&mdbg, dbg_n * 8); }
         cudaMemsetAsync(mdbg, 0, dbg_n * 8, st);
@@ -691,6 +691,24 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
             for (int j = 0; j < (k == 1 ? 4 : 5); ++j) { snprintf(buf, sizeof buf, "L3 %s %s", nm[k], sub[j]); stat(8 + 8 * k + j, buf); }
         }
         stat(3, "head done"); stat(4, "barrier passed");
+        {   // per-warp stamps of one CTA (77): min / max over the 16 warps, relative to the phase's first stamp
+            const char* wn[11] = {"start", "prepoll", "A loaded", "ssq out", "sync1", "normed", "mma", "red out", "sync2", "reduced", "end"};
+            const char* pn[5] = {"qkv", "attn", "wo", "w13", "w2"};
+            for (int ph = 0; ph < 5; ++ph) {
+                if (ph == 1) continue;
+                const long long* w = t.data() + (size_t)G * 64 + (size_t)ph * 256;
+                long long base = 0;
+                for (int k = 0; k < 16; ++k) if (w[k * 16] && (!base || w[k * 16] < base)) base = w[k * 16];
+                if (!base) continue;
+                fprintf(stderr, "[pk warp] %-3s", pn[ph]);
+                for (int sI = 0; sI < 11; ++sI) {
+                    long long mn = 0, mx = 0;
+                    for (int k = 0; k < 16; ++k) { const long long v = w[k * 16 + sI]; if (!v) continue; if (!mn || v < mn) mn = v; if (v > mx) mx = v; }
+                    if (mn) fprintf(stderr, " | %s %.2f-%.2f", wn[sI], (mn - base) * 1e-3, (mx - base) * 1e-3);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
     }
     return CAR_OK;
 }

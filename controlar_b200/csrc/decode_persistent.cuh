@@ -25,7 +25,7 @@
 #include "sampler.cuh"
 
 constexpr int PK_WARPS = 16, PK_THREADS = PK_WARPS * 32;
-constexpr int PK_NSLOT = 8;                          // ring slots
+constexpr int PK_NSLOT = 8;                          // ring slots (power of two)
 constexpr int PK_UNIT_KS = 40;                       // k32-steps per streamed unit (one 8-column block, <= 40 steps)
 constexpr int PK_SLOT_BYTES = PK_UNIT_KS * 512;      // 20 KB
 constexpr int PK_NBMAX = 4;                          // 8-column blocks per batch (accumulator registers)
@@ -196,7 +196,7 @@ __device__ __forceinline__ void pk_stream_issue(const PkParams& P, const PkSmem&
 // A operand: poll the tagged packets of this warp's k-steps (s = warp + 16 i) straight into mma fragments
 // ---------------------------------------------------------------------------------------------------------
 // one round: up to 4 k-steps = 16 x 16 B per lane in flight
-template <int I0, int CNT>
+template <int I0, int CNT, bool FULL>
 __device__ __forceinline__ void pk_poll_round(const unsigned char* __restrict__ base, int nst, int warp, int lane, unsigned int tag,
                                               bool need_lo, bool need_hi, uint32_t (&alo)[PK_MAXA][4], uint32_t (&ahi)[PK_MAXA][4]) {
     // k-steps past the end re-read step 0 and are ignored (unconditional first loads keep the 16-byte results in registers);
@@ -216,7 +216,7 @@ __device__ __forceinline__ void pk_poll_round(const unsigned char* __restrict__ 
         for (int u = 0; u < CNT; ++u) {
             unsigned int b = 0;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) b |= (need_lo ? (v[u][p].y ^ tag) : 0u) | (need_hi ? (v[u][p].w ^ tag) : 0u);
+            for (int p = 0; p < 4; ++p) b |= ((FULL || need_lo) ? (v[u][p].y ^ tag) : 0u) | ((FULL || need_hi) ? (v[u][p].w ^ tag) : 0u);
             if (I0 + u < nst && b != 0u) {
                 any_bad = true;
 #pragma unroll
@@ -232,8 +232,8 @@ __device__ __forceinline__ void pk_poll_round(const unsigned char* __restrict__ 
         const bool in = I0 + u < nst;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            alo[I0 + u][p] = (in && need_lo) ? v[u][p].x : 0u;
-            ahi[I0 + u][p] = (in && need_hi) ? v[u][p].z : 0u;
+            alo[I0 + u][p] = (in && (FULL || need_lo)) ? v[u][p].x : 0u;
+            ahi[I0 + u][p] = (in && (FULL || need_hi)) ? v[u][p].z : 0u;
         }
     }
 }
@@ -280,7 +280,7 @@ __device__ __forceinline__ const bf16* pk_ctrl_next(const PkParams& P, int l) {
 }
 
 __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& sm, const int kind, const int l, const int pos,
-                                              const unsigned int tag, int blk_lo, int blk_hi, unsigned int& cons, long long* dbg) {
+                                              const unsigned int tag, int blk_lo, int blk_hi, unsigned int& cons, long long* dbg, long long* wdbg_base) {
     const int par = l & 1;
     const bool NORM = (kind == 0 || kind == 2 || kind == 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -289,9 +289,20 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
     const int nsub = (KS + PK_UNIT_KS - 1) / PK_UNIT_KS;
     const int nst = (KS - warp + PK_WARPS - 1) / PK_WARPS;
     const int M = P.b_eff;
+#ifdef PK_TRACE
     const bool stamp = dbg != nullptr && tid == 0;
+#else
+    constexpr bool stamp = false;
+#endif
     if (blk_lo >= blk_hi) return;                      // this CTA owns no columns of this phase
     if (stamp) dbg[0] = pk_now();
+    long long* const wdbg = (wdbg_base != nullptr && lane == 0) ? wdbg_base + warp * 16 : nullptr;   // per-warp stamps (dev)
+#ifdef PK_TRACE
+#define PK_W(k) do { if (wdbg) wdbg[k] = pk_now(); } while (0)
+#else
+#define PK_W(k) do { } while (0)
+#endif
+    PK_W(0);
 
     // epilogue identity of this thread (fixed across batches): block ej of the batch, row pair eg, column pair ecp
     const int ej = tid >> 7, eq = tid & 127, ei = eq >> 2, er = eq & 3, eg = ei >> 2, ecp = ei & 3;
@@ -330,18 +341,27 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                     nwv[i] = i < nst ? __ldg(reinterpret_cast<const uint4*>(nw + (warp + i * PK_WARPS) * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
             }
             pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3);
-            pk_poll_round<0, PK_MAXA_NORM>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
+            PK_W(1);
+            if (M == 16) pk_poll_round<0, PK_MAXA_NORM, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
+            else pk_poll_round<0, PK_MAXA_NORM, false>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
 #pragma unroll
             for (int i = PK_MAXA_NORM; i < PK_MAXA; ++i)
 #pragma unroll
                 for (int p = 0; p < 4; ++p) { alo[i][p] = 0u; ahi[i][p] = 0u; }
         } else {
             pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3);
-            pk_poll_round<0, 4>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
-            pk_poll_round<4, 3>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
+            PK_W(1);
+            if (M == 16) {
+                pk_poll_round<0, 4, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
+                pk_poll_round<4, 3, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
+            } else {
+                pk_poll_round<0, 4, false>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
+                pk_poll_round<4, 3, false>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
+            }
         }
     }
     if (stamp) dbg[1] = pk_now();
+    PK_W(2);
     if (NORM) {
         float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
@@ -363,8 +383,10 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         if (kind == 2 && nb > 1) nb &= ~1;             // w1/w3 blocks travel in pairs
         const int nunits = nb * nsub;
         // ---- wait for the batch's weight units (one thread per unit); ssq partials become visible
+        if (first) PK_W(3);
         if (tid < nunits) { const unsigned int u = cons + tid; pk_mbar_wait(&sm.full[u % PK_NSLOT], (u / PK_NSLOT) & 1); }
         __syncthreads();
+        if (first) PK_W(4);
         if (NORM && first) {
             float q_lo = 0.f, q_hi = 0.f;
 #pragma unroll
@@ -393,26 +415,33 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
             }
         }
         if (stamp && first) dbg[2] = pk_now();
-        // ---- MMA: this warp's k-steps against the batch's blocks, B fragments from the ring
+        if (first) PK_W(5);
+        // ---- MMA: this warp's k-steps against the batch's blocks, B fragments from the ring (32-bit shared addresses;
+        // the unit of (block j, sub-unit) sits in slot (cons + j nsub + sub) mod 8)
         float acc[PK_NBMAX][4];
 #pragma unroll
         for (int j = 0; j < PK_NBMAX; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+        const uint32_t ring_s = pk_smem(sm.ring) + lane * 16;
 #pragma unroll
         for (int i = 0; i < PK_MAXA; ++i) {
             if (i < nst) {
                 const int s = warp + i * PK_WARPS;
                 const int sub = s / PK_UNIT_KS, so = s - sub * PK_UNIT_KS;
+                const uint32_t u0 = cons + sub;
+                const uint32_t koff = ring_s + so * 512;
 #pragma unroll
                 for (int j = 0; j < PK_NBMAX; ++j) {
                     if (j < nb) {
-                        const unsigned int u = cons + j * nsub + sub;
-                        const uint4 wf = *reinterpret_cast<const uint4*>(sm.ring + (size_t)(u % PK_NSLOT) * PK_SLOT_BYTES + so * 512 + lane * 16);
+                        uint4 wf;
+                        const uint32_t addr = koff + ((u0 + j * nsub) & (PK_NSLOT - 1)) * PK_SLOT_BYTES;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wf.x), "=r"(wf.y), "=r"(wf.z), "=r"(wf.w) : "r"(addr));
                         mma_bf16_16816(acc[j], alo[i][0], ahi[i][0], alo[i][1], ahi[i][1], wf.x, wf.y);
                         mma_bf16_16816(acc[j], alo[i][2], ahi[i][2], alo[i][3], ahi[i][3], wf.z, wf.w);
                     }
                 }
             }
         }
+        if (first) PK_W(6);
 #pragma unroll
         for (int j = 0; j < PK_NBMAX; ++j) {
             if (j < nb) {
@@ -421,8 +450,10 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                 *reinterpret_cast<float2*>(rp + 80 + g * 8 + 2 * t) = make_float2(acc[j][2], acc[j][3]);
             }
         }
+        if (first) PK_W(7);
         __syncthreads();
         if (stamp && first) dbg[3] = pk_now();
+        if (first) PK_W(8);
         cons += nunits;
         if (tid == PK_THREADS - 32) {                  // the batch's slots are free again: keep the stream ahead
             PkStream& st = *sm.st;
@@ -448,6 +479,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                     val = rnd<bf16>(silu_f(rnd<bf16>(val))) * rnd<bf16>(val3);
                 }
             }
+            if (first) PK_W(9);
             const int qb = lane & ~3;
             const float v00 = val;
             const float v01 = __shfl_sync(0xffffffffu, val, qb + 1);
@@ -508,6 +540,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
             }
         }
         if (stamp && first) dbg[4] = pk_now();
+        if (first) PK_W(10);
         b0 += nb;
         first = false;
     }
@@ -587,7 +620,11 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     const int G = (int)min((long long)gridDim.x, tot);     // every participating CTA gets at least one key
     if ((int)blockIdx.x >= G) return;
     const long long f0 = ((long long)blockIdx.x * tot) / G, f1 = ((long long)(blockIdx.x + 1) * tot) / G;
+#ifdef PK_TRACE
     const bool stamp = dbg != nullptr && tid == 0;
+#else
+    constexpr bool stamp = false;
+#endif
     if (stamp) dbg[0] = pk_now();
     const int pair_lo = (int)(f0 / n), pair_hi = (int)((f1 - 1) / n);
     const int nseg = min(pair_hi - pair_lo + 1, PK_MAXSEG);   // host guarantees <= PK_MAXSEG
@@ -826,7 +863,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
     for (int step = 0; step < P.n_steps; ++step) {
         const int pos = P.T - 1 + step;                    // logits of this position are sampled now
         const unsigned int tag0 = P.tag_base + (unsigned int)step * tstride + 1u;   // tag(step, 0)
+#ifdef PK_TRACE
         const bool dbg_step = P.dbg != nullptr && step == P.dbg_step;
+#else
+        constexpr bool dbg_step = false;
+#endif
         long long* const dbg_cta = P.dbg + (size_t)blockIdx.x * 64;
         if (dbg_step && tid == 0) dbg_cta[0] = pk_now();
         // ---------------- sampler (+ embedding of the sampled token for position pos + 1) ----------------
@@ -857,7 +898,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
                 long long* dbg = (dbg_step && l == 3) ? dbg_cta + 8 + 8 * ph : nullptr;
                 if (l < P.L && ph == 1) { pk_attn_phase(P, sm, l, p, tag, par, dbg); continue; }
                 const int kind = l == P.L ? 4 : (ph == 0 ? 0 : ph - 1);
-                pk_gemm_phase(P, sm, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg);
+                pk_gemm_phase(P, sm, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg,
+                              (dbg != nullptr && (int)blockIdx.x == 77 % (int)gridDim.x) ? P.dbg + (size_t)gridDim.x * 64 + (size_t)ph * 256 : nullptr);
             }
         }
         if (dbg_step && tid == 0) dbg_cta[3] = pk_now();
