@@ -11,6 +11,7 @@
 #include "sampler.cuh"
 #include "misc.cuh"
 #include "decode_persistent.cuh"
+#include "gemm_dense.cuh"
 #include <algorithm>
 
 thread_local std::string g_car_err;
@@ -67,6 +68,7 @@ struct CarState {
     float cs;
     // prefill scratch
     void *hP, *qP, *attnP, *actP, *t1, *t2;
+    void *qkvP, *gP, *uP;     // dense prefill path (bf16): qkv [rows][3d], w1 / w3 outputs [rows][F]
     bool prefilled;
     // decode graph
     cudaGraphExec_t gexec;
@@ -355,6 +357,8 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     for (int j = 0; j < 3; ++j) A(&s->ctrl[j], MC * dd * es);
     A(&s->hP, MP * dd * es); A(&s->qP, MP * dd * es); A(&s->attnP, MP * dd * es); A(&s->actP, MP * F * es);
     A(&s->t1, std::max(MC, MP) * dd * es); A(&s->t2, std::max(MC, MP) * dd * es);
+    s->qkvP = s->gP = s->uP = nullptr;
+    if (d.dtype == CAR_BF16) { A(&s->qkvP, MP * 3 * dd * es); A(&s->gP, MP * F * es); A(&s->uP, MP * F * es); }
     A((void**)&s->emb_mask, MP * 4);
     if (r == CAR_OK && cudaMemset(s->tickets, 0, (size_t)b_eff * d.n_head * 4) != cudaSuccess) r = CAR_ERR_CUDA;
     if (r == CAR_OK && cudaMemset(s->pos, 0, 16) != cudaSuccess) r = CAR_ERR_CUDA;
@@ -428,6 +432,46 @@ static EpiParams epi_base(int kind) {
     return ep;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// dense (M >= 128 rows) bf16 path of the prefill: tiled tensor-core GEMM on the ORIGINAL [N][K] weights
+// ---------------------------------------------------------------------------------------------------------
+static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, int M, int N, int K, int act, const void* resid, int ldr,
+                        void* out, int ldo) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+        attr_set = true;
+    }
+    if (M <= 0 || N <= 0) return CAR_OK;
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = (const bf16*)A; p.B = (const bf16*)W; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = K; p.C = out; p.ldc = ldo; p.alpha = 1.f;
+    p.amode = A_PLAIN; p.act = act; p.resid = (const bf16*)resid; p.ldr = ldr; p.out_mode = 0;
+    dim3 grid((N + DG_BN - 1) / DG_BN, (M + DG_BM - 1) / DG_BM, 1);
+    CAR_LAUNCH(dense_gemm_kernel, grid, DG_THREADS, DG_SMEM, st, p);
+    return CAR_OK;
+}
+static bool use_dense(const CarState* s, int rows) { return s->m->d.dtype == CAR_BF16 && rows >= 64 && s->qkvP != nullptr; }
+
+// one prefill block on the dense path (same rounding points as the skinny chain)
+static int enqueue_block_dense(CarState* s, int l, cudaStream_t st) {
+    CarModel* m = s->m;
+    const CarModelDesc& d = m->d;
+    const int dim = d.dim, F = d.ffn_dim, rows = s->b_eff * s->T;
+    CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)s->hP, (const bf16*)m->attention_norm[l], (bf16*)s->t1, dim, d.norm_eps);
+    CAR_TRY(dense_linear(st, s->t1, dim, m->wqkv[l], rows, 3 * dim, dim, ACT_NONE, nullptr, 0, s->qkvP, 3 * dim));
+    CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)s->qkvP, s->rope, (bf16*)s->qP, (bf16*)s->kc[l], (bf16*)s->vc[l], rows, s->T, dim,
+               d.n_head, s->S);
+    CAR_TRY(launch_attn_prefill<bf16>(s, l, st));
+    CAR_TRY(dense_linear(st, s->attnP, dim, m->wo[l], rows, dim, dim, ACT_NONE, s->hP, dim, s->hP, dim));
+    CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)s->hP, (const bf16*)m->ffn_norm[l], (bf16*)s->t1, dim, d.norm_eps);
+    CAR_TRY(dense_linear(st, s->t1, dim, m->w1[l], rows, F, dim, ACT_NONE, nullptr, 0, s->gP, F));
+    CAR_TRY(dense_linear(st, s->t1, dim, m->w3[l], rows, F, dim, ACT_NONE, nullptr, 0, s->uP, F));
+    CAR_LAUNCH(swiglu_kernel, 148 * 8, 256, 0, st, (const bf16*)s->gP, (const bf16*)s->uP, (bf16*)s->actP, (long long)rows * F);
+    CAR_TRY(dense_linear(st, s->actP, F, m->w2[l], rows, dim, F, ACT_NONE, s->hP, dim, s->hP, dim));
+    return CAR_OK;
+}
+
 // one transformer block on `rows` rows; decode (rpb = 1, pos from device scalar) or prefill (rpb = T, pos = t)
 static int enqueue_block(CarState* s, int l, bool decode, cudaStream_t st) {
     CarModel* m = s->m;
@@ -489,9 +533,13 @@ static int enqueue_decode_layers(CarState* s, float* logits, cudaStream_t st) {
     return enqueue_head(s, s->h, s->b_eff, logits, st);
 }
 
-static int enqueue_mlp(CarState* s, const void* x, int rows, int K, const void* fc1, const void* fc2, void* tmp, void* out,
-                       cudaStream_t st) {
+static int enqueue_mlp(CarState* s, const void* x, int rows, int K, const void* fc1, const void* fc2, const void* fc1_plain,
+                       const void* fc2_plain, void* tmp, void* out, cudaStream_t st) {
     const CarModelDesc& d = s->m->d;
+    if (use_dense(s, rows) && K % 8 == 0) {      // MLP.forward gpt_t2i.py:165-181: fc2(gelu_tanh(fc1 x)), bias-free
+        CAR_TRY(dense_linear(st, x, K, fc1_plain, rows, d.dim, K, ACT_GELU_TANH, nullptr, 0, tmp, d.dim));
+        return dense_linear(st, tmp, d.dim, fc2_plain, rows, d.dim, d.dim, ACT_NONE, nullptr, 0, out, d.dim);
+    }
     EpiParams a = epi_base(EPI_STORE);
     a.out = tmp; a.ldo = d.dim; a.act = 1;
     CAR_TRY(launch_skinny(st, d.dtype, x, K, fc1, nullptr, 0.f, rows, d.dim, K, a, false));
@@ -520,7 +568,7 @@ extern "C" int car_prefill(CarState* s, const void* cond, const void* condition,
     s->has_ctrl = condition != nullptr;
     s->graph_ok = false;
     // 1. prefix embeddings: CaptionEmbedder MLP (gpt_t2i.py:156-162) or LabelEmbedder gather (:89-97)
-    if (d.model_type == 1) CAR_TRY(enqueue_mlp(s, cond, rows, d.caption_dim, m->g_cap_fc1, m->g_cap_fc2, s->t1, s->hP, st));
+    if (d.model_type == 1) CAR_TRY(enqueue_mlp(s, cond, rows, d.caption_dim, m->g_cap_fc1, m->g_cap_fc2, m->cap_fc1, m->cap_fc2, s->t1, s->hP, st));
     else {
         if (d.dtype == CAR_BF16) CAR_LAUNCH((gather_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)m->label_table, (const int*)cond, (bf16*)s->hP, d.dim, (const bf16*)nullptr, 0, 0, 0.f);
         else CAR_LAUNCH((gather_rows_kernel<float>), rows, 256, 0, st, (const float*)m->label_table, (const int*)cond, (float*)s->hP, d.dim, (const float*)nullptr, 0, 0, 0.f);
@@ -528,13 +576,15 @@ extern "C" int car_prefill(CarState* s, const void* cond, const void* condition,
     // 2. control tokens: condition_mlp then the three condition_layers MLPs (gpt_t2i.py:438-442)
     if (condition) {
         const int crow = s->b_eff * s->N;
-        CAR_TRY(enqueue_mlp(s, condition, crow, d.dim, m->g_cond_fc1, m->g_cond_fc2, s->t1, s->t2, st));
-        for (int j = 0; j < 3; ++j) CAR_TRY(enqueue_mlp(s, s->t2, crow, d.dim, m->g_ctl_fc1[j], m->g_ctl_fc2[j], s->t1, s->ctrl[j], st));
+        CAR_TRY(enqueue_mlp(s, condition, crow, d.dim, m->g_cond_fc1, m->g_cond_fc2, m->cond_fc1, m->cond_fc2, s->t1, s->t2, st));
+        for (int j = 0; j < 3; ++j)
+            CAR_TRY(enqueue_mlp(s, s->t2, crow, d.dim, m->g_ctl_fc1[j], m->g_ctl_fc2[j], m->ctl_fc1[j], m->ctl_fc2[j], s->t1, s->ctrl[j], st));
     }
     // 3. blocks
     for (int l = 0; l < d.n_layer; ++l) {
         if (d.dtype == CAR_BF16) CAR_TRY(prefill_small_kernels<bf16>(s, l, st)); else CAR_TRY(prefill_small_kernels<float>(s, l, st));
-        CAR_TRY(enqueue_block(s, l, false, st));
+        if (use_dense(s, rows)) CAR_TRY(enqueue_block_dense(s, l, st));
+        else CAR_TRY(enqueue_block(s, l, false, st));
     }
     // 4. head: last prefix row always (feeds car_generate); all rows on request (forward() parity)
     if (d.dtype == CAR_BF16) CAR_LAUNCH((take_last_row_kernel<bf16>), s->b_eff, 256, 0, st, (const bf16*)s->hP, (bf16*)s->h, s->T, d.dim);

@@ -54,7 +54,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // ldmatrix (8 rows x 16 B) and the 16-B cp.async stores are bank-conflict free.
 __device__ __forceinline__ int dg_off(int row, int chunk) { return row * DG_BK + ((chunk ^ ((row >> 1) & 3)) << 3); }
 
-__global__ void __launch_bounds__(DG_THREADS) dense_gemm_kernel(DenseP p) {
+static __global__ void __launch_bounds__(DG_THREADS) dense_gemm_kernel(DenseP p) {   // (static: one copy per translation unit)
     extern __shared__ __align__(128) unsigned char dg_smem[];
     bf16* sA = reinterpret_cast<bf16*>(dg_smem);
     bf16* sB = sA + DG_STAGES * DG_BM * DG_BK;
