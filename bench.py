@@ -177,6 +177,7 @@ def run_ours(args):
     from controlar_b200.autoregressive.models.gpt_t2i import GPT_models
     from controlar_b200.autoregressive.models.generate import generate
     from controlar_b200.tokenizer.tokenizer_image.vq_model import VQ_models
+    from controlar_b200.parallel import gather_token_grids, rank_seed
     from oracle.inputs import text_inputs, control_map     # seeded synthetic inputs only (no oracle compute here)
 
     torch.manual_seed(0)
@@ -203,10 +204,8 @@ def run_ours(args):
         else:
             c, m, x = cond_d, masks_d, cmap_d
         # rank seed mirrors sample_c2i_ddp.py:47 (global_seed * world + rank), advanced per step
-        toks = generate(gpt, c, N, emb_masks=m, condition=x, seed=(step_idx * world + rank), **kw)
-        if world > 1:
-            allt = torch.empty((world * B, N), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(allt, toks)      # the single NCCL all-gather of finished token grids
+        toks = generate(gpt, c, N, emb_masks=m, condition=x, seed=rank_seed(step_idx, world, rank), **kw)
+        allt = gather_token_grids(toks)                  # the single NCCL all-gather of finished token grids (world > 1)
         img = vq.decode_code(toks, [B, 8, g, g])
         if host_io:
             img_h.copy_(img, non_blocking=True)
@@ -283,7 +282,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                     "kernel": "decode loop (36x{qkv,attn,wo,w13,w2} + head + sampler per token, CUDA-graph replay)",
+                     "kernel": "pk_decode_kernel: persistent decode loop (per token 36 x {qkv | attention | wo | w1w3 | w2} + head + CFG/top-k sampler), one launch per generate()",
                      "algorithmic_bytes": step_bytes, "decode_ms": dec_ms, "ms_per_token": dec_ms / (N - 1)},
         "clocks": clk,
     }

@@ -126,7 +126,8 @@ int car_sample(const float* logits, int32_t b_eff, int32_t V, const CarSampling*
 
 /* ---- device-side generation loop: generate()'s prefill-sample + decode_n_tokens (generate.py:113-131,
  * 195-204).  Must follow car_prefill(...) on the same state.  Runs n_tokens sampling steps (the first one on
- * the prefill logits) as a replayed CUDA graph with no host synchronisation; tokens_out int32 [B, n_tokens].
+ * the prefill logits) with no host synchronisation — bf16, B_eff <= 16: ONE persistent cooperative kernel
+ * (csrc/decode_persistent.cuh); otherwise a replayed CUDA graph of the per-kernel chain.  tokens_out int32 [B, n_tokens].
  * noise: optional fp32 [n_tokens, B, V]. ---- */
 int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise,
                  int32_t* tokens_out, void* stream);
