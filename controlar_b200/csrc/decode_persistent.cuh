@@ -334,12 +334,6 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pk_a_buf(P, kind, par));
         const bool need_lo = g < M, need_hi = g + 8 < M;
         if (kind != 3) {
-            if (NORM) {
-                const bf16* nw = kind == 0 ? P.attn_norm[l] : kind == 2 ? P.ffn_norm[l] : P.norm_w;
-#pragma unroll
-                for (int i = 0; i < PK_MAXA_NORM; ++i)
-                    nwv[i] = i < nst ? __ldg(reinterpret_cast<const uint4*>(nw + (warp + i * PK_WARPS) * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
-            }
             pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3);
             PK_W(1);
             if (M == 16) pk_poll_round<0, PK_MAXA_NORM, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
@@ -362,6 +356,13 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
     }
     if (stamp) dbg[1] = pk_now();
     PK_W(2);
+    {   // norm weights: requested after the poll (before it they would be spilled across it), used after the CTA barrier;
+        // unconditional definition (a conditionally initialised array would live in local memory)
+        const bf16* nw = kind == 0 ? P.attn_norm[l] : kind == 2 ? P.ffn_norm[l] : P.norm_w;
+#pragma unroll
+        for (int i = 0; i < PK_MAXA_NORM; ++i)
+            nwv[i] = (NORM && i < nst) ? __ldg(reinterpret_cast<const uint4*>(nw + (warp + i * PK_WARPS) * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
+    }
     if (NORM) {
         float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
@@ -369,8 +370,8 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 float a, b;
-                unpack_bf16x2(alo[i][p], a, b); s_lo += a * a + b * b;
-                unpack_bf16x2(ahi[i][p], a, b); s_hi += a * a + b * b;
+                unpack_bf16x2(alo[i][p], a, b); s_lo = fmaf(a, a, s_lo); s_lo = fmaf(b, b, s_lo);
+                unpack_bf16x2(ahi[i][p], a, b); s_hi = fmaf(a, a, s_hi); s_hi = fmaf(b, b, s_hi);
             }
         s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
         s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
@@ -388,10 +389,12 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         __syncthreads();
         if (first) PK_W(4);
         if (NORM && first) {
-            float q_lo = 0.f, q_hi = 0.f;
+            // row sums of squares: lane i adds row (i & 15) over the 16 warps in order, rsqrt, then rows g / g + 8 by shuffle
+            float qs = 0.f;
 #pragma unroll
-            for (int w = 0; w < PK_WARPS; ++w) { q_lo += sm.ssq[w * 16 + g]; q_hi += sm.ssq[w * 16 + g + 8]; }
-            const float r_lo = rsqrtf(q_lo / (float)K + P.eps), r_hi = rsqrtf(q_hi / (float)K + P.eps);
+            for (int w = 0; w < PK_WARPS; ++w) qs += sm.ssq[w * 16 + (lane & 15)];
+            const float rs = rsqrtf(qs / (float)K + P.eps);
+            const float r_lo = __shfl_sync(0xffffffffu, rs, g), r_hi = __shfl_sync(0xffffffffu, rs, g + 8);
 #pragma unroll
             for (int i = 0; i < PK_MAXA_NORM; ++i) {
                 if (i < nst) {
