@@ -766,24 +766,29 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     }
     __syncthreads();
     if (stamp) dbg[2] = pk_now();
-    // ---- finalise: two warps per segment (thread e = dimension) merge the entries of their pair in (warp, part) order
+    // ---- finalise: two warps per segment (thread e = dimension) merge the entries of their pair in warp order.  Only the
+    // warps whose range touches the pair are visited (a handful, not all 32 entries): this section runs on two warps alone.
     {
         const int sg = warp >> 1, e = tid & 63;
         if (sg < nseg) {
             const PkSeg q = pk_segment(P, sg, nseg, pair_lo, f0, f1, n);
+            const long long R = f1 - f0, Cw = (R + PK_WARPS - 1) / PK_WARPS;
+            const long long ps = max(f0, (long long)q.bh * n), pe = min(f1, (long long)(q.bh + 1) * n);
+            const int w0 = (int)((ps - f0) / Cw), w1 = (int)((pe - 1 - f0) / Cw);
+            const long long pair_start = (long long)q.bh * n;
             float Mx = -INFINITY;
-#pragma unroll 4
-            for (int i = 0; i < 2 * PK_WARPS; ++i)
-                if (__float_as_int(sc[i * ENT]) == q.bh) Mx = fmaxf(Mx, sc[i * ENT + 1]);
+            for (int w = w0; w <= w1; ++w) {
+                const int part = (f0 + (long long)w * Cw >= pair_start) ? 0 : 1;   // the warp range starts inside this pair, or in the one before
+                Mx = fmaxf(Mx, sc[(w * 2 + part) * ENT + 1]);
+            }
             float Ls = 0.f, a = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < 2 * PK_WARPS; ++i) {
-                if (__float_as_int(sc[i * ENT]) == q.bh) {
-                    const float mi = sc[i * ENT + 1];
-                    const float wt = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
-                    Ls += sc[i * ENT + 2] * wt;
-                    a += sc[i * ENT + 4 + e] * wt;
-                }
+            for (int w = w0; w <= w1; ++w) {
+                const int part = (f0 + (long long)w * Cw >= pair_start) ? 0 : 1;   // the warp range starts inside this pair, or in the one before
+                const float* en = sc + (w * 2 + part) * ENT;
+                const float mi = en[1];
+                const float wt = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
+                Ls += en[2] * wt;
+                a += en[4 + e] * wt;
             }
             pk_attn_finalize(P, Mx, Ls, a, q, e, n, tot, G, tag, par);
         }

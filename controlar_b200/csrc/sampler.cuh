@@ -163,14 +163,27 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
     if (a.top_k > 0 && a.top_k < V) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) zr[j] = __uint_as_float((tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u);
+        // two key bits per step: count the elements >= cand | (1,2,3 << shift) together; one CTA barrier per step
+        // (the per-warp counts go through alternating halves of the scratch array)
+        __shared__ unsigned red_c[2][THREADS / 32][3];
         unsigned cand = 0;
 #pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-            const unsigned tryv = cand | (1u << bit);
-            unsigned c = 0;
+        for (int shift = 30, it = 0; shift >= 0; shift -= 2, ++it) {
+            const unsigned t1 = cand | (1u << shift), t2 = cand | (2u << shift), t3 = cand | (3u << shift);
+            unsigned c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) c += __float_as_uint(zr[j]) >= tryv ? 1u : 0u;
-            if (smp_block_count<THREADS>(c, red_u) >= (unsigned)a.top_k) cand = tryv;
+            for (int j = 0; j < EPT; ++j) {
+                const unsigned k = __float_as_uint(zr[j]);
+                c1 += k >= t1 ? 1u : 0u; c2 += k >= t2 ? 1u : 0u; c3 += k >= t3 ? 1u : 0u;
+            }
+            c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+            if (lane == 0) { red_c[it & 1][warp][0] = c1; red_c[it & 1][warp][1] = c2; red_c[it & 1][warp][2] = c3; }
+            __syncthreads();
+            unsigned s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) { s1 += red_c[it & 1][w][0]; s2 += red_c[it & 1][w][1]; s3 += red_c[it & 1][w][2]; }
+            const unsigned kk = (unsigned)a.top_k;                 // counts are non-increasing in the threshold
+            cand = s3 >= kk ? t3 : (s2 >= kk ? t2 : (s1 >= kk ? t1 : cand));
         }
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
