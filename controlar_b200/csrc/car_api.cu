@@ -732,6 +732,7 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
             fprintf(stderr, "[pk] %-22s n=%3zu  min %8.2f  med %8.2f  max %8.2f us (CTA %d)\n", name, v.size(), v.front() * 1e-3, v[v.size() / 2] * 1e-3,
                     v.back() * 1e-3, amax);
         };
+        if (!t[0] && !t[64]) fprintf(stderr, "[pk] no stamps: rebuild with CAR_PK_TRACE=1 (python -m controlar_b200.build --force)\n");
         fprintf(stderr, "[pk] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
         stat(0, "step start"); stat(1, "sampler done");
         const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};

@@ -241,7 +241,7 @@ __device__ __forceinline__ void pk_poll_round(const unsigned char* __restrict__ 
 // Cheap arrival hint before the full poll: warp 0 watches the first packet of 32 of the K/8 producer blocks (a different
 // subset per CTA) with back-off; the other warps wait at the CTA barrier.  148 x 32 eight-byte loads per round instead of
 // the whole tile from every waiting thread — waiting CTAs must not eat the L2 bandwidth of the ones still producing.
-__device__ __forceinline__ void pk_prepoll(const uint2* buf, int K, unsigned int tag, int mode) {
+__device__ __forceinline__ void pk_prepoll(const uint2* buf, int K, unsigned int tag, int mode, unsigned mode_sleep) {
     if (mode == 1) return;                             // (experiment) straight to the full poll
     const int nblk = K >> 3;
     if (mode == 2) {                                   // (experiment) every warp watches one packet of its own first k-step
@@ -256,7 +256,8 @@ __device__ __forceinline__ void pk_prepoll(const uint2* buf, int K, unsigned int
     if (threadIdx.x < 32) {
         const uint2* pkt = buf + pk_a_index(0, (int)((blockIdx.x * 7u + threadIdx.x * (unsigned)max(1, nblk >> 5)) % (unsigned)nblk) * 8);
         unsigned int spins = 0;
-        while (!__all_sync(0xffffffffu, pk_ld64(pkt).y == tag)) { __nanosleep(120); pk_spin_check(spins); }
+        const unsigned ns = mode_sleep;
+        while (!__all_sync(0xffffffffu, pk_ld64(pkt).y == tag)) { __nanosleep(ns); pk_spin_check(spins); }
     }
     __syncthreads();
 }
@@ -334,7 +335,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pk_a_buf(P, kind, par));
         const bool need_lo = g < M, need_hi = g + 8 < M;
         if (kind != 3) {
-            pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3);
+            pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3, ((P.exp_flags >> 8) & 15) == 0 ? 120u : 20u * ((P.exp_flags >> 8) & 15));
             PK_W(1);
             if (M == 16) pk_poll_round<0, PK_MAXA_NORM, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
             else pk_poll_round<0, PK_MAXA_NORM, false>(base, nst, warp, lane, tag, need_lo, need_hi, alo, ahi);
@@ -343,7 +344,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
 #pragma unroll
                 for (int p = 0; p < 4; ++p) { alo[i][p] = 0u; ahi[i][p] = 0u; }
         } else {
-            pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3);
+            pk_prepoll(pk_a_buf(P, kind, par), K, tag, P.exp_flags & 3, ((P.exp_flags >> 8) & 15) == 0 ? 120u : 20u * ((P.exp_flags >> 8) & 15));
             PK_W(1);
             if (M == 16) {
                 pk_poll_round<0, 4, true>(base, nst, warp, lane, tag, true, true, alo, ahi);
