@@ -713,6 +713,10 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
                     kraw[u] = ldg_cg128(kbase + (size_t)rr * 64); vraw[u] = ldg_cg128(vbase + (size_t)rr * 64);
                     msk[u] = (mrow != nullptr && rr < P.T) ? __ldg(mrow + rr) : 1;
                 }
+                // scores of the block's (up to 8) keys first, ONE running-max update and rescale per block, then the
+                // probability-weighted sum: exp(s - m) and 8 FFMA per key (soft-max is invariant to the reference maximum)
+                float sc8[UNR];
+                float mb = -INFINITY;
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
                     const int r = rb + sub + 4 * u;
@@ -727,19 +731,26 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
 #pragma unroll
                     for (int e = 0; e < EPL; ++e) s = fmaf(qf[e], kf[e], s);
                     s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    s *= 0.125f;                                // 1/sqrt(head_dim = 64)
-                    if (r < k1 && msk[u] != 0) {
+                    sc8[u] = (r < k1 && msk[u] != 0) ? s * 0.125f : -INFINITY;      // 1/sqrt(head_dim = 64); masked / past-the-end -> weight 0
+                    mb = fmaxf(mb, sc8[u]);
+                }
+                const float m_new = fmaxf(m_run, mb);
+                if (m_new != -INFINITY) {                     // (uniform over the 8 lanes of a row slot)
+                    const float corr = __expf(m_run - m_new);   // exp(-inf) = 0 on the first block
+                    l_run *= corr;
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) acc[e] *= corr;
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
                         float vf[EPL];
                         unpack_bf16x2(vraw[u].x, vf[0], vf[1]); unpack_bf16x2(vraw[u].y, vf[2], vf[3]);
                         unpack_bf16x2(vraw[u].z, vf[4], vf[5]); unpack_bf16x2(vraw[u].w, vf[6], vf[7]);
-                        const float m_new = fmaxf(m_run, s);
-                        const float corr = __expf(m_run - m_new);
-                        const float p = __expf(s - m_new);
-                        l_run = l_run * corr + p;
+                        const float p = __expf(sc8[u] - m_new);
+                        l_run += p;
 #pragma unroll
-                        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
-                        m_run = m_new;
+                        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
                     }
+                    m_run = m_new;
                 }
             }
             // merge the warp's four row slots (lanes 8 apart), fixed order
