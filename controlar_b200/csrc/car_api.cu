@@ -12,6 +12,7 @@
 #include "misc.cuh"
 #include "decode_persistent.cuh"
 #include "gemm_dense.cuh"
+#include "gemm_tc5.cuh"
 #include <algorithm>
 
 thread_local std::string g_car_err;
@@ -443,6 +444,22 @@ static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, 
         attr_set = true;
     }
     if (M <= 0 || N <= 0) return CAR_OK;
+    static const bool use_tc5 = [] { const char* e = getenv("CAR_TC5"); return e ? atoi(e) != 0 : true; }();
+    if (use_tc5 && K % T5_BK == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (resid == nullptr || ldr % 8 == 0)) {
+        // tcgen05 path (gemm_tc5.cuh): accumulator in TMEM, operands through shared-memory descriptors
+        static bool attr5 = false;
+        if (!attr5) {
+            CAR_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+            attr5 = true;
+        }
+        Tc5P q;
+        memset(&q, 0, sizeof(q));
+        q.A = (const bf16*)A; q.B = (const bf16*)W; q.M = M; q.N = N; q.K = K; q.lda = lda; q.ldb = K;
+        q.resid = (const bf16*)resid; q.ldr = ldr; q.C = (bf16*)out; q.ldc = ldo; q.act = act == ACT_GELU_TANH ? 1 : 0;
+        dim3 grid5((N + T5_BN - 1) / T5_BN, (M + T5_BM - 1) / T5_BM, 1);
+        CAR_LAUNCH(gemm_tc5_kernel, grid5, T5_THREADS, T5_SMEM, st, q);
+        return CAR_OK;
+    }
     DenseP p;
     memset(&p, 0, sizeof(p));
     p.A = (const bf16*)A; p.B = (const bf16*)W; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = K; p.C = out; p.ldc = ldo; p.alpha = 1.f;
