@@ -287,7 +287,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(img_h.numel() * 4)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                     "traffic": None, "traffic_note": "ncu --set full of a 24-token launch (profiles/r1_pk_decode_final_ncu.csv): dram read+write = 1.02 x algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                      "kernel": "pk_decode_kernel: persistent decode loop (per token 36 x {qkv | attention | wo | w1w3 | w2} + head + CFG/top-k sampler), one launch per generate()",
                      "algorithmic_bytes": step_bytes, "decode_ms": dec_ms, "ms_per_token": dec_ms / (N - 1)},
         "clocks": clk,

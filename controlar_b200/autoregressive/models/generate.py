@@ -1,6 +1,7 @@
 """Drop-in for the reference ``autoregressive/models/generate.py``: same ``generate()`` signature and return
 value (int32 [B, max_new_tokens]), but prefill, the N-1 decode steps, CFG, top-k/top-p and sampling all run on
-the device behind ``car_prefill`` + ``car_generate`` (one CUDA-graph replay per token, no host sync in the loop).
+the device behind ``car_prefill`` + ``car_generate`` (bf16: ONE persistent kernel launch for the whole decode loop;
+fp32 / unsupported shapes: one CUDA-graph replay per token; no host sync in the loop either way).
 
 Deviations, on purpose and documented in DESIGN.md:
   * sampled runs draw their exponential noise from an in-kernel Philox stream seeded from torch's generator

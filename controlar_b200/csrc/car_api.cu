@@ -18,7 +18,9 @@
 thread_local std::string g_car_err;
 std::atomic<long long> g_car_launches{0};
 
-// development knobs (environment, read once): CAR_PDL, CAR_L2PF, CAR_NSPLIT, CAR_NB_QKV/WO/W13/W2/HEAD
+// development knobs (environment, read once): CAR_MEGA (0 = per-kernel graph chain instead of the persistent decode kernel),
+// CAR_DBG (trace step; needs a -DPK_TRACE build), CAR_EXP (experiment bits of decode_persistent.cuh), CAR_TC5 (0 = mma.sync dense
+// GEMM in the prefill), CAR_PDL, CAR_L2PF, CAR_NSPLIT, CAR_NB_QKV/WO/W13/W2/HEAD (per-kernel chain)
 struct Tune { int pdl, l2pf, nsplit, nb[5], skip, empty, dbg, mega, mega_pf; };
 static long long* g_dbg = nullptr;   // [5 kernels][8] clock stamps (CAR_DBG=1)
 __global__ void empty_kernel(int) {}

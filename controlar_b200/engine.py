@@ -102,7 +102,8 @@ class ARModelHandle:
 
 
 class ARStateHandle:
-    """CarState: KV caches (PyTorch-owned, reference layout), control tokens, scratch, decode CUDA graph."""
+    """CarState: KV caches (PyTorch-owned, reference layout), control tokens, scratch, the persistent decode kernel's packet
+    buffers (and the CUDA graph of the per-kernel fallback chain)."""
 
     def __init__(self, model: ARModelHandle, b_eff: int, S: int, N: int, k_caches, v_caches, rope: torch.Tensor):
         self.lib = model.lib

@@ -8,7 +8,8 @@ from controlar_b200 import _lib
 
 torch.manual_seed(0)
 B = int(os.environ.get("B", 8)); N = int(os.environ.get("N", 1024)); cfg = float(os.environ.get("CFG", 4.0))
-m = GPT_models["GPT-XL"](block_size=1024, cls_token_num=120, model_type="t2i").eval()
+SIDE = int(os.environ.get("SIDE", 32))          # RoPE table side: 32 (512x512), 48 (--image-size 768, config 4)
+m = GPT_models["GPT-XL"](block_size=SIDE * SIDE, cls_token_num=120, model_type="t2i").eval()
 m.output.weight.data.normal_(0, 0.02)
 m = m.to("cuda", torch.bfloat16)
 m.adapter.forward = lambda x: x
