@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--height", type=int, default=0, help="non-square generation (config 4: --height 512 --width 768); default --size")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--adapter-size", default="small", choices=["small", "base"], help="DINOv2-small (config 2) or -base (config 3)")
+    ap.add_argument("--condition-type", default="canny", help="canny | depth | hed | lineart | seg (config 3: depth)")
     ap.add_argument("--model", default="GPT-XL")
     ap.add_argument("--cfg-scale", type=float, default=4.0)
     ap.add_argument("--top-k", type=int, default=2000)
@@ -187,18 +191,21 @@ def run_ours(args):
     from oracle.inputs import text_inputs, control_map     # seeded synthetic inputs only (no oracle compute here)
 
     torch.manual_seed(0)
-    g = args.size // 16
-    N, T, B = g * g, 120, args.batch
-    gpt = GPT_models[args.model](block_size=N, cls_token_num=T, model_type="t2i", condition_type="canny", adapter_size="small").eval()
+    H_img, W_img = (args.height or args.size), (args.width or args.size)
+    gh, gw = H_img // 16, W_img // 16
+    g = max(gh, gw)                                   # RoPE table side = image_size / 16 (sample_t2i_MR.py:72-74)
+    N, T, B = gh * gw, 120, args.batch
+    gpt = GPT_models[args.model](block_size=g * g, cls_token_num=T, model_type="t2i", condition_type=args.condition_type,
+                                 adapter_size=args.adapter_size).eval()
     gpt.output.weight.data.normal_(0, 0.02)          # the reference zero-inits the head (gpt_t2i.py:377)
     for blk in gpt.adapter.model.encoder.layer:      # HF init has layerscale 1.0
         blk.layer_scale1.lambda1.data.fill_(1.0); blk.layer_scale2.lambda1.data.fill_(1.0)
     gpt = gpt.to(dev, torch.bfloat16)
     vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).to(dev).eval()
     cond_h, masks_h = text_inputs(T, 2048, B, 1000 + rank, torch.bfloat16)
-    cmap_h = control_map(B, args.size, args.size, 2000 + rank, "canny", torch.bfloat16)
+    cmap_h = control_map(B, H_img, W_img, 2000 + rank, args.condition_type, torch.bfloat16)
     cond_h, masks_h, cmap_h = cond_h.pin_memory(), masks_h.pin_memory(), cmap_h.pin_memory()
-    img_h = torch.empty((B, 3, args.size, args.size), dtype=torch.float32).pin_memory()
+    img_h = torch.empty((B, 3, H_img, W_img), dtype=torch.float32).pin_memory()
     cond_d, masks_d, cmap_d = cond_h.to(dev), masks_h.to(dev), cmap_h.to(dev)
     kw = dict(cfg_scale=args.cfg_scale, temperature=1.0, top_k=args.top_k, top_p=1.0, sample_logits=True)
     lib = _lib.lib()
@@ -212,7 +219,7 @@ def run_ours(args):
         # rank seed mirrors sample_c2i_ddp.py:47 (global_seed * world + rank), advanced per step
         toks = generate(gpt, c, N, emb_masks=m, condition=x, seed=rank_seed(step_idx, world, rank), **kw)
         allt = gather_token_grids(toks)                  # the single NCCL all-gather of finished token grids (world > 1)
-        img = vq.decode_code(toks, [B, 8, g, g])
+        img = vq.decode_code(toks, [B, 8, gh, gw])
         if host_io:
             img_h.copy_(img, non_blocking=True)
         return toks, img
@@ -277,8 +284,8 @@ def run_ours(args):
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (args.model, args.size, args.batch) == ("GPT-XL", 512, 8) else
-                   f"{args.model} t2i + DINOv2-small canny, {args.size}x{args.size}, batch={args.batch}/GPU",
+        "config": {"workload": WORKLOAD if (args.model, H_img, W_img, args.batch, args.adapter_size, args.condition_type) == ("GPT-XL", 512, 512, 8, "small", "canny") else
+                   f"{args.model} t2i + DINOv2-{args.adapter_size} {args.condition_type}, {W_img}x{H_img}, batch={args.batch}/GPU",
                    "global_batch": world * B, "tokens_per_image": N, "parallelism": f"dp{world} (batch sharded, one all-gather of token grids)",
                    "l2": "working set larger than L2 (weights 1.5 GB + KV cache up to 3.4 GB stream every decode step)",
                    "sampling": {"cfg_scale": args.cfg_scale, "top_k": args.top_k, "temperature": 1.0, "top_p": 1.0}},
