@@ -161,7 +161,10 @@ def run_reference(args):
     line = {"metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": n_warm,
             "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "global_batch": args.batch, "l2": "inputs larger than L2 (weights 1.5 GB + KV 3.4 GB)"},
+            "config": {"workload": WORKLOAD, "global_batch": args.gpus * args.batch, "tokens_per_image": (args.size // 16) ** 2,
+                       "parallelism": f"dp{args.gpus} (batch sharded, one all-gather of token grids)",
+                       "l2": "working set larger than L2 (weights 1.5 GB + KV cache up to 3.4 GB stream every decode step)",
+                       "sampling": {"cfg_scale": args.cfg_scale, "top_k": args.top_k, "temperature": 1.0, "top_p": 1.0}},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
