@@ -6,7 +6,9 @@
   Dinov2SelfAttention (sdpa), Dinov2MLP, Dinov2LayerScale).
 * ``vq_decode_oracle`` / ``vq_encode_oracle`` restate VQModel.decode_code / encode
   (tokenizer/tokenizer_image/vq_model.py:41-56,129-195,65-125,198-277,280-397).
-Pinned by tests/golden/dinov2.pt and tests/golden/vq16.pt, which were produced by the reference modules.
+* ``vit_adapter_oracle`` restates ViT_Adapter.forward (autoregressive/models/vit_adapter.py:13-15, HF ViTModel) — the
+  control encoder of the legacy c2i class ``gpt.py`` (oracle only, no CUDA path yet).
+Pinned by tests/golden/dinov2.pt, tests/golden/vit.pt and tests/golden/vq16.pt, which were produced by the reference modules.
 """
 from __future__ import annotations
 
@@ -53,6 +55,45 @@ def dinov2_adapter_oracle(sd: Dict[str, torch.Tensor], x: torch.Tensor, conditio
         y = F.linear(F.gelu(F.linear(y, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])), w[p + "mlp.fc2.weight"],
                      w[p + "mlp.fc2.bias"])
         hs = y * w[p + "layer_scale2.lambda1"] + hs
+    hs = F.layer_norm(hs, (C,), w["layernorm.weight"], w["layernorm.bias"], eps)
+    return hs[:, 1:]
+
+
+def vit_adapter_oracle(sd: Dict[str, torch.Tensor], x: torch.Tensor, dtype, heads: int = 6, layers: int = 12,
+                       eps: float = 1e-12, prefix: str = "model.") -> torch.Tensor:
+    """ViT_Adapter.forward (autoregressive/models/vit_adapter.py:13-15): HF ViTModel(x, interpolate_pos_encoding=True)
+    .last_hidden_state[:, 1:] — restated from the installed transformers 5.5.0 modeling_vit.py (ViTEmbeddings.forward /
+    interpolate_pos_encoding :60-128, ViTLayer :315-346, ViTSelfAttention :199-252 (sdpa), final layernorm).  No input
+    resize, patch 16, no LayerScale, position table interpolated in the MODEL dtype (Dinov2 interpolates in fp32)."""
+    w = {k[len(prefix):]: v.to(dtype) for k, v in sd.items() if k.startswith(prefix)}
+    x = x.to(dtype)
+    B, _, H, W = x.shape
+    P = w["embeddings.patch_embeddings.projection.weight"].shape[-1]
+    e = F.conv2d(x, w["embeddings.patch_embeddings.projection.weight"], w["embeddings.patch_embeddings.projection.bias"],
+                 stride=P).flatten(2).transpose(1, 2)
+    C = e.shape[-1]
+    e = torch.cat([w["embeddings.cls_token"].expand(B, -1, -1), e], dim=1)
+    pos = w["embeddings.position_embeddings"]
+    G = int(round((pos.shape[1] - 1) ** 0.5))
+    h, wd = H // P, W // P
+    if not (h * wd == G * G and H == W):
+        pp = pos[:, 1:].reshape(1, G, G, C).permute(0, 3, 1, 2)
+        pp = F.interpolate(pp, size=(h, wd), mode="bicubic", align_corners=False)
+        pos = torch.cat([pos[:, :1], pp.permute(0, 2, 3, 1).reshape(1, -1, C)], dim=1)
+    hs = e + pos
+    for l in range(layers):
+        p = f"encoder.layer.{l}."
+        y = F.layer_norm(hs, (C,), w[p + "layernorm_before.weight"], w[p + "layernorm_before.bias"], eps)
+        q = F.linear(y, w[p + "attention.attention.query.weight"], w[p + "attention.attention.query.bias"])
+        k = F.linear(y, w[p + "attention.attention.key.weight"], w[p + "attention.attention.key.bias"])
+        v = F.linear(y, w[p + "attention.attention.value.weight"], w[p + "attention.attention.value.bias"])
+        sh = lambda t: t.view(B, -1, heads, C // heads).transpose(1, 2)
+        a = F.scaled_dot_product_attention(sh(q), sh(k), sh(v), scale=(C // heads) ** -0.5)
+        a = a.transpose(1, 2).reshape(B, -1, C)
+        hs = F.linear(a, w[p + "attention.output.dense.weight"], w[p + "attention.output.dense.bias"]) + hs
+        y = F.layer_norm(hs, (C,), w[p + "layernorm_after.weight"], w[p + "layernorm_after.bias"], eps)
+        y = F.gelu(F.linear(y, w[p + "intermediate.dense.weight"], w[p + "intermediate.dense.bias"]))
+        hs = F.linear(y, w[p + "output.dense.weight"], w[p + "output.dense.bias"]) + hs
     hs = F.layer_norm(hs, (C,), w["layernorm.weight"], w["layernorm.bias"], eps)
     return hs[:, 1:]
 

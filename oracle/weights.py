@@ -97,6 +97,39 @@ def dinov2_shapes(hidden: int, layers: int = 12, mlp_ratio: int = 4, patch: int 
     return {prefix + k: v for k, v in s.items()}
 
 
+def vit_shapes(hidden: int = 384, layers: int = 12, intermediate: int = 1536, patch: int = 16, image: int = 224,
+               prefix: str = "", pooler: bool = True) -> Dict[str, Tuple[int, ...]]:
+    """HF ViTModel keys (transformers/models/vit/modeling_vit.py, installed 5.5.0) — the encoder behind the legacy c2i class's
+    ViT_Adapter (autoregressive/models/vit_adapter.py:11)."""
+    n_pos = (image // patch) ** 2 + 1
+    s: Dict[str, Tuple[int, ...]] = {
+        "embeddings.cls_token": (1, 1, hidden),
+        "embeddings.position_embeddings": (1, n_pos, hidden),
+        "embeddings.patch_embeddings.projection.weight": (hidden, 3, patch, patch),
+        "embeddings.patch_embeddings.projection.bias": (hidden,),
+        "layernorm.weight": (hidden,),
+        "layernorm.bias": (hidden,),
+    }
+    if pooler:
+        s["pooler.dense.weight"] = (hidden, hidden)
+        s["pooler.dense.bias"] = (hidden,)
+    for i in range(layers):
+        q = f"encoder.layer.{i}."
+        for n in ("layernorm_before", "layernorm_after"):
+            s[q + n + ".weight"] = (hidden,)
+            s[q + n + ".bias"] = (hidden,)
+        for n in ("query", "key", "value"):
+            s[q + f"attention.attention.{n}.weight"] = (hidden, hidden)
+            s[q + f"attention.attention.{n}.bias"] = (hidden,)
+        s[q + "attention.output.dense.weight"] = (hidden, hidden)
+        s[q + "attention.output.dense.bias"] = (hidden,)
+        s[q + "intermediate.dense.weight"] = (intermediate, hidden)
+        s[q + "intermediate.dense.bias"] = (intermediate,)
+        s[q + "output.dense.weight"] = (hidden, intermediate)
+        s[q + "output.dense.bias"] = (hidden,)
+    return {prefix + k: v for k, v in s.items()}
+
+
 def gpt_shapes(spec: GPTSpec, with_adapter: bool = True, dino_layers: int = 12) -> Dict[str, Tuple[int, ...]]:
     d, F, V = spec.dim, spec.ffn_dim, spec.vocab_size
     s: Dict[str, Tuple[int, ...]] = {}
@@ -136,7 +169,8 @@ def _fill(shapes: Dict[str, Tuple[int, ...]], seed: int, linear_std: float) -> D
     out: Dict[str, torch.Tensor] = {}
     for k, shp in shapes.items():
         if k.endswith("norm.weight") or k.endswith("norm1.weight") or k.endswith("norm2.weight") \
-                or k.endswith("norm_out.weight") or k.endswith("layernorm.weight"):
+                or k.endswith("norm_out.weight") or k.endswith("layernorm.weight") or k.endswith("layernorm_before.weight") \
+                or k.endswith("layernorm_after.weight"):
             out[k] = _randn(k, shp, 0.1, seed, mean=1.0)
         elif k.endswith("lambda1"):
             out[k] = _randn(k, shp, 0.2, seed, mean=1.0)

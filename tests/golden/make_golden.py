@@ -206,6 +206,96 @@ def dino_case():
     print("dino ok", flush=True)
 
 
+@contextlib.contextmanager
+def fake_vit_cwd(layers: int = 12):
+    """vit_adapter.py:11 loads 'autoregressive/models/vit-small' relative to CWD (ViT-S/16: hidden 384, 6 heads, MLP 1536)."""
+    from transformers import ViTConfig, ViTModel
+    cfg = ViTConfig(hidden_size=384, num_hidden_layers=layers, num_attention_heads=6, intermediate_size=1536, patch_size=16,
+                    image_size=224, qkv_bias=True, layer_norm_eps=1e-12, hidden_act="gelu")
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "autoregressive", "models", "vit-small")
+        os.makedirs(d)
+        ViTModel(cfg).save_pretrained(d)
+        os.chdir(tmp)
+        try:
+            yield
+        finally:
+            os.chdir(old)
+
+
+def vit_case():
+    """ViT_Adapter (the control encoder of the legacy c2i class gpt.py): outputs for square and non-square inputs."""
+    from autoregressive.models.vit_adapter import ViT_Adapter
+    from oracle.weights import vit_shapes, _fill
+    out = {"header": header(), "seed": 9, "layers": 4}
+    sd = _fill(vit_shapes(384, layers=4, prefix="model."), 9, 0.02)
+    with fake_vit_cwd(4), contextlib.redirect_stdout(io.StringIO()):
+        ad = ViT_Adapter()
+    assert set(ad.state_dict()) == set(sd), set(ad.state_dict()) ^ set(sd)
+    ad.load_state_dict(sd)
+    ad.eval()
+    for dt in (torch.float32, torch.bfloat16):
+        a = ad.to(dt)
+        for (H, W) in ((224, 224), (64, 64), (64, 96)):
+            x = control_map(2, H, W, 23, "canny", dt)
+            with torch.no_grad():
+                out[f"{str(dt).split('.')[-1]}_{H}x{W}_out"] = a(x).clone()
+        ad.to(torch.float32)
+    torch.save(out, os.path.join(OUT, "vit.pt"))
+    print("vit ok", flush=True)
+
+
+def gptpy_case():
+    """The LEGACY c2i class autoregressive/models/gpt.py (ViT adapter, per-step condition_layers, no control_strength) run
+    through the reference generate() with cfg_scale 1.0 (gpt.py + CFG raises TypeError), bf16 (gpt.py:427
+    hard-casts the control tokens to bf16).  Pins the claim that its inference arithmetic equals the gpt_t2i class with
+    model_type='c2i' given the same adapter_mlp output."""
+    from autoregressive.models.gpt import Transformer, ModelArgs
+    from autoregressive.models.generate import generate
+    from oracle.weights import vit_shapes, _fill
+    seed, B, H, W, dtype = 0, 2, 64, 64, torch.bfloat16
+    spec = GPTSpec(**SMALL, cls_token_num=1, block_size=(H // 16) * (W // 16), model_type="c2i")
+    with fake_vit_cwd(2), contextlib.redirect_stdout(io.StringIO()):
+        m = Transformer(ModelArgs(dim=spec.dim, n_layer=spec.n_layer, n_head=spec.n_head, multiple_of=spec.multiple_of,
+                                  vocab_size=spec.vocab_size, cls_token_num=1, block_size=spec.block_size,
+                                  num_classes=spec.num_classes, model_type="c2i", condition_token_num=0, image_size=H))
+    sd = make_gpt_state_dict(spec, seed, with_adapter=False)
+    ref_sd = m.state_dict()
+    extra = {k for k in ref_sd if k not in sd}
+    assert all(k.startswith("adapter.model.") or k == "condition_norm.weight" for k in extra), extra
+    assert all(k in ref_sd and tuple(ref_sd[k].shape) == tuple(v.shape) for k, v in sd.items()), "gpt.py key/shape mismatch"
+    full = dict(sd)
+    full.update(_fill(vit_shapes(384, layers=2, prefix="adapter.model."), seed, 0.02))
+    full["condition_norm.weight"] = torch.ones(spec.dim)
+    m.load_state_dict(full, strict=True)
+    m = m.to(dtype).eval()
+    N = spec.block_size
+    cond = class_inputs(spec.num_classes, B, seed + 1)
+    cmap = control_map(B, H, W, seed + 2, "canny", dtype)
+    with torch.no_grad():
+        feat = m.adapter(cmap)
+        ctrl_in = m.adapter_mlp(feat)
+    rec = []
+    orig_forward = m.forward
+
+    def spy(*a, **k):
+        lg, loss = orig_forward(*a, **k)
+        rec.append(lg[:, -1].clone())
+        return lg, loss
+    m.forward = spy
+    with math_sdpa():
+        greedy = generate(m, cond, N, cfg_scale=1.0, condition=cmap, temperature=1.0, top_k=0, top_p=1.0, sample_logits=False)
+    m.forward = orig_forward
+    raw = torch.stack(rec, dim=1)
+    out = {"header": header(), "spec": spec.__dict__, "seed": seed, "dtype": str(dtype), "B": B, "H": H, "W": W, "cfg_scale": 1.0,
+           "control_strength": 1.0, "class": "autoregressive/models/gpt.py Transformer (legacy c2i class), ViT layers = 2",
+           "adapter_out": feat, "ctrl_in": ctrl_in, "greedy_tokens": greedy.clone(), "raw_logits_all": raw.to(dtype).clone(),
+           "raw_logits_absmax": raw.abs().amax(dim=-1)}
+    torch.save(out, os.path.join(OUT, "c2i_gptpy_bf16.pt"))
+    print("gptpy greedy", tuple(greedy.shape), "raw", tuple(raw.shape), flush=True)
+
+
 SMALL = dict(dim=256, n_layer=6, n_head=4, vocab_size=2048)
 
 CASES = {
@@ -240,6 +330,8 @@ CASES = {
     "sampler": sampler_case,
     "vq16": vq_case,
     "dinov2": dino_case,
+    "vit": vit_case,
+    "c2i_gptpy_bf16": gptpy_case,
 }
 
 if __name__ == "__main__":

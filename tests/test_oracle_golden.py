@@ -35,9 +35,12 @@ def test_oracle_fp32_bit_exact_greedy_and_logits(name):
     assert rel_l2(z, zr) < 5e-6
 
 
-@pytest.mark.parametrize("name", ["t2i_small_bf16", "c2i_small_bf16", "t2i_mr_bf16", "t2i_mr_tall_bf16"])
+@pytest.mark.parametrize("name", ["t2i_small_bf16", "c2i_small_bf16", "t2i_mr_bf16", "t2i_mr_tall_bf16", "c2i_gptpy_bf16"])
 def test_oracle_bf16_teacher_forced(name):
-    """bf16: teacher-forced along the reference trajectory; tolerance = bf16 noise floor."""
+    """bf16: teacher-forced along the reference trajectory; tolerance = bf16 noise floor.
+    c2i_gptpy_bf16 was produced by the LEGACY class autoregressive/models/gpt.py (ViT adapter, condition_layers applied per step,
+    no control_strength): the gpt_t2i-style oracle with model_type='c2i' reproduces it from the adapter_mlp output, i.e. the
+    two classes share their inference arithmetic."""
     g = load_golden(name)
     orc, cond, masks, N = _run_oracle(g)
     spec = orc.spec
@@ -112,3 +115,20 @@ def test_vision_oracles_vs_reference():
     assert rel_l2(img, v["image_mr"]) < 1e-4
     idx, z, _ = vq_encode_oracle(vsd, v["image_mr"].clamp(-1, 1))
     assert (idx == v["enc_idx_mr"]).float().mean() > 0.99
+
+
+def test_vit_adapter_oracle_vs_reference():
+    """ViT_Adapter (HF ViT-S/16, interpolate_pos_encoding) restatement against the reference module's outputs — square at the
+    native grid (no interpolation), square small and non-square (bicubic position table)."""
+    from oracle.weights import vit_shapes, _fill
+    from oracle.inputs import control_map
+    from oracle.vision_oracle import vit_adapter_oracle
+    g = load_golden("vit")
+    sd = _fill(vit_shapes(384, layers=g["layers"], prefix="model."), g["seed"], 0.02)
+    for (H, W) in ((224, 224), (64, 64), (64, 96)):
+        x = control_map(2, H, W, 23, "canny", torch.float32)
+        got = vit_adapter_oracle(sd, x, torch.float32, heads=6, layers=g["layers"])
+        assert got.shape == g[f"float32_{H}x{W}_out"].shape
+        assert rel_l2(got, g[f"float32_{H}x{W}_out"]) < 1e-4, (H, W)
+        gotb = vit_adapter_oracle(sd, x.to(torch.bfloat16), torch.bfloat16, heads=6, layers=g["layers"])
+        assert rel_l2(gotb.float(), g[f"bfloat16_{H}x{W}_out"].float()) < 3e-2, (H, W)
