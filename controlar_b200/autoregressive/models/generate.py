@@ -52,7 +52,7 @@ def generate(model, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_int
              **sampling_kwargs):
     """Reference generate.py:134-204."""
     if condition is not None:
-        if getattr(model.adapter, "forward", None) is not None and type(model.adapter).__name__ == "Dinov2_Adapter" \
+        if getattr(model.adapter, "forward", None) is not None and type(model.adapter).__name__ in ("Dinov2_Adapter", "ViT_Adapter") \
                 and "forward" not in vars(model.adapter) and "forward" not in vars(model.adapter_mlp):
             # generate.py:137-138 as one library call: DINOv2 forward + adapter_mlp on the dense tensor-core path
             from ... import vision as _vision

@@ -167,7 +167,7 @@ class Transformer(nn.Module):
         self.vocab_size, self.n_layer, self.block_size = config.vocab_size, config.n_layer, config.block_size
         self.num_classes, self.model_type, self.cls_token_num = config.num_classes, config.model_type, config.cls_token_num
         self.layer_internal = config.n_layer // 3
-        self.adapter = Dinov2_Adapter(adapter_size=config.adapter_size, condition_type=config.condition_type)
+        self.adapter = self._make_adapter(config)
         self.adapter_mlp = MLP(384 if config.adapter_size == "small" else 768, config.dim, config.dim)
         if self.model_type == "c2i":
             self.cls_embedding = LabelEmbedder(config.num_classes, config.dim, config.class_dropout_prob)
@@ -194,6 +194,10 @@ class Transformer(nn.Module):
         self._car_model: Optional[_engine.ARModelHandle] = None
         self._car_state: Optional[_engine.ARStateHandle] = None
         self._n_img = self.block_size
+
+    def _make_adapter(self, config: ModelArgs) -> nn.Module:
+        """Control encoder (gpt_t2i.py:326-333): DINOv2; the legacy c2i class (gpt.py) overrides this with ViT-S/16."""
+        return Dinov2_Adapter(adapter_size=config.adapter_size, condition_type=config.condition_type)
 
     # same init distribution as the reference (gpt_t2i.py:366-388): N(0, 0.02) Linear/Embedding, zero head
     def initialize_weights(self):

@@ -49,7 +49,8 @@ struct CarDino {
     CarDinoDesc d;
     std::vector<void*> owned;
     // bf16 GEMM-ready weights
-    bf16* w_patch;                      // [C][608]
+    bf16* w_patch;                      // [C][kpad]  (k = 3 * patch^2 = 588 -> 608 for DINOv2, 768 for ViT-S/16)
+    int kpatch, kpad;
     const void *b_patch, *cls, *pos, *ln_w, *ln_b;
     struct Layer { bf16 *w_qk, *b_qk, *w_v; const void *b_v, *w_o, *b_o, *ls1, *ls2, *n1w, *n1b, *n2w, *n2b, *w_fc1, *b_fc1, *w_fc2, *b_fc2; };
     std::vector<Layer> L;
@@ -73,22 +74,24 @@ extern "C" int car_dino_create(const CarDinoDesc* desc, const CarDinoWeights* w,
     if (!desc || !w || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
     const CarDinoDesc& d = *desc;
     if (d.hidden % 64 || d.heads * 64 != d.hidden) CAR_FAIL(CAR_ERR_UNSUPPORTED, "DINOv2 head_dim must be 64");
-    if (d.patch != 14) CAR_FAIL(CAR_ERR_UNSUPPORTED, "patch size must be 14");
+    if (d.patch != 14 && d.patch != 16) CAR_FAIL(CAR_ERR_UNSUPPORTED, "patch size must be 14 (DINOv2) or 16 (ViT-S/16)");
     cudaStream_t st = (cudaStream_t)stream;
     CarDino* m = new CarDino();
     m->d = d;
     const int C = d.hidden, dt = d.dtype;
     int r = CAR_OK;
     auto T = [&](int rc) { if (r == CAR_OK) r = rc; };
-    // patch projection [C][3*14*14] -> [C][608] zero padded
+    // patch projection [C][3*P*P] -> [C][kpad] zero padded (k-tiles of 32)
+    m->kpatch = 3 * d.patch * d.patch;
+    m->kpad = (m->kpatch + 31) & ~31;
     {
         bf16* tmp = nullptr;
-        T(to_bf16_any(st, dt, m->owned, w->patch_w, (long long)C * 588, &tmp));
-        if (r == CAR_OK && cudaMalloc((void**)&m->w_patch, (size_t)C * 608 * 2) != cudaSuccess) r = CAR_ERR_CUDA;
+        T(to_bf16_any(st, dt, m->owned, w->patch_w, (long long)C * m->kpatch, &tmp));
+        if (r == CAR_OK && cudaMalloc((void**)&m->w_patch, (size_t)C * m->kpad * 2) != cudaSuccess) r = CAR_ERR_CUDA;
         if (r == CAR_OK) {
             m->owned.push_back(m->w_patch);
-            cudaMemsetAsync(m->w_patch, 0, (size_t)C * 608 * 2, st);
-            cudaMemcpy2DAsync(m->w_patch, 608 * 2, tmp, 588 * 2, 588 * 2, C, cudaMemcpyDeviceToDevice, st);
+            cudaMemsetAsync(m->w_patch, 0, (size_t)C * m->kpad * 2, st);
+            cudaMemcpy2DAsync(m->w_patch, (size_t)m->kpad * 2, tmp, (size_t)m->kpatch * 2, (size_t)m->kpatch * 2, C, cudaMemcpyDeviceToDevice, st);
         }
     }
     auto cv = [&](const void* src, long long n) -> const void* {   // bf16 view of a (possibly fp32) vector / matrix
@@ -145,13 +148,14 @@ static int dino_forward_t(CarDino* m, const TI* image, int B, int H, int W, void
     // workspace
     size_t need = 0;
     auto sz = [&](size_t b) { need += (b + 255) & ~(size_t)255; };
-    sz((size_t)B * hw * 608 * 2); sz((size_t)B * hw * C * 2); sz((size_t)hw * C * 2);
+    const int KP = m->kpad;
+    sz((size_t)B * hw * KP * 2); sz((size_t)B * hw * C * 2); sz((size_t)hw * C * 2);
     sz(rows * C * 2); sz(rows * C * 2); sz(rows * 2 * C * 2); sz((size_t)B * C * Tp * 2);
     sz((size_t)B * heads * Tn * Tp * 4); sz((size_t)B * heads * Tn * Tp * 2); sz(rows * C * 2); sz(rows * 4 * C * 2);
     sz((size_t)B * hw * C * 2); sz((size_t)B * hw * std::max(m->ad_dim, 1) * 2);
     CAR_TRY(m->ws.reserve(need));
     m->ws.reset();
-    bf16* patches = (bf16*)m->ws.take((size_t)B * hw * 608 * 2);
+    bf16* patches = (bf16*)m->ws.take((size_t)B * hw * KP * 2);
     bf16* ptok = (bf16*)m->ws.take((size_t)B * hw * C * 2);
     bf16* posi = (bf16*)m->ws.take((size_t)hw * C * 2);
     bf16* x = (bf16*)m->ws.take(rows * C * 2);
@@ -166,10 +170,10 @@ static int dino_forward_t(CarDino* m, const TI* image, int B, int H, int W, void
     bf16* mlp_h = (bf16*)m->ws.take((size_t)B * hw * std::max(m->ad_dim, 1) * 2);
 
     CAR_CUDA(cudaMemsetAsync(vT, 0, (size_t)B * C * Tp * 2, st));   // padded key columns must be finite (x 0 prob)
-    // 1. resize to (h*14, w*14) + patchify (dinov2_adapter.py:16-24), patch projection + bias
-    CAR_LAUNCH((resize_patchify_kernel<TI>), gsz((long long)B * hw * 608), 256, 0, st, image, patches, B, H, W, h, w, 608, d.resize_mode);
+    // 1. resize to (h*P, w*P) + patchify (dinov2_adapter.py:16-24; ViT: P = 16, no resize), patch projection + bias
+    CAR_LAUNCH((resize_patchify_kernel<TI>), gsz((long long)B * hw * KP), 256, 0, st, image, patches, B, H, W, h, w, KP, d.resize_mode, d.patch);
     {
-        DenseP p = dp_plain(patches, 608, m->w_patch, 608, B * hw, C, 608, ptok, C);
+        DenseP p = dp_plain(patches, KP, m->w_patch, KP, B * hw, C, KP, ptok, C);
         p.bias = (const bf16*)m->b_patch;
         CAR_TRY(dense(st, p));
     }

@@ -117,8 +117,8 @@ __global__ void cast_to_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__
         y[i] = fromf<bf16>(tof(x[i]));
 }
 
-// ---- control-map resize to multiples of 14 (dinov2_adapter.py:16-24) fused with the 14x14 patch im2col:
-// out[b*hw + py*w + px][c*196 + ky*14 + kx] (Kpad columns, zero padded) = resized[b][c][py*14+ky][px*14+kx]
+// ---- control-map resize to multiples of the patch size P (dinov2_adapter.py:16-24) fused with the PxP patch im2col:
+// out[b*hw + py*w + px][c*P*P + ky*P + kx] (Kpad columns, zero padded) = resized[b][c][py*P+ky][px*P+kx]
 // mode 0: F.interpolate(mode='nearest')  src = floor(dst * in/out)
 // mode 1: bicubic, align_corners=True (A = -0.75), computed in fp32 and rounded to the model dtype like
 //         upsample_bicubic2d on a bf16 tensor (opmath float, output cast)
@@ -126,17 +126,19 @@ __device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; retur
 __device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
 template <typename TI>
 __global__ void resize_patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int h, int w,
-                                       int Kpad, int mode) {
-    const int nh = h * 14, nw = w * 14;
+                                       int Kpad, int mode, int P) {
+    // P = patch size: 14 (DINOv2: the map is first resized to (h*14, w*14)) or 16 (ViT-S/16 of the legacy c2i class,
+    // vit_adapter.py:13-15: no resize — with nh == H the nearest mode below is the identity)
+    const int nh = h * P, nw = w * P, PP = P * P;
     const long long total = (long long)B * h * w * Kpad;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i % Kpad);
         const long long row = i / Kpad;
         float v = 0.f;
-        if (k < 588) {
-            const int c = k / 196, r = k % 196, ky = r / 14, kx = r % 14;
+        if (k < 3 * PP) {
+            const int c = k / PP, r = k % PP, ky = r / P, kx = r % P;
             const int px = (int)(row % w), py = (int)((row / w) % h), b = (int)(row / ((long long)w * h));
-            const int oy = py * 14 + ky, ox = px * 14 + kx;
+            const int oy = py * P + ky, ox = px * P + kx;
             const TI* src = img + ((size_t)b * 3 + c) * H * W;
             if (mode == 0) {
                 const int sy = min((int)floorf(oy * ((float)H / nh)), H - 1);

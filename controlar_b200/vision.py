@@ -80,7 +80,22 @@ class DinoHandle:
         w.patch_w, w.patch_b = P(e.patch_embeddings.projection.weight), P(e.patch_embeddings.projection.bias)
         w.ln_w, w.ln_b = P(m.layernorm.weight), P(m.layernorm.bias)
         layers = list(m.encoder.layer)
-        get = {
+        is_vit = hasattr(layers[0], "layernorm_before")      # HF ViTModel key names (vit_adapter.py) vs Dinov2Model
+        if is_vit:
+            ones = torch.ones(m.hidden, dtype=dt, device=m.layernorm.weight.device)     # no LayerScale in ViT: x 1 is exact
+            keep.append(ones)
+            get = {
+                "n1_w": lambda b: b.layernorm_before.weight, "n1_b": lambda b: b.layernorm_before.bias,
+                "q_w": lambda b: b.attention.attention.query.weight, "q_b": lambda b: b.attention.attention.query.bias,
+                "k_w": lambda b: b.attention.attention.key.weight, "k_b": lambda b: b.attention.attention.key.bias,
+                "v_w": lambda b: b.attention.attention.value.weight, "v_b": lambda b: b.attention.attention.value.bias,
+                "o_w": lambda b: b.attention.output.dense.weight, "o_b": lambda b: b.attention.output.dense.bias,
+                "ls1": lambda b: ones, "n2_w": lambda b: b.layernorm_after.weight, "n2_b": lambda b: b.layernorm_after.bias,
+                "fc1_w": lambda b: b.intermediate.dense.weight, "fc1_b": lambda b: b.intermediate.dense.bias,
+                "fc2_w": lambda b: b.output.dense.weight, "fc2_b": lambda b: b.output.dense.bias, "ls2": lambda b: ones,
+            }
+        else:
+          get = {
             "n1_w": lambda b: b.norm1.weight, "n1_b": lambda b: b.norm1.bias,
             "q_w": lambda b: b.attention.attention.query.weight, "q_b": lambda b: b.attention.attention.query.bias,
             "k_w": lambda b: b.attention.attention.key.weight, "k_b": lambda b: b.attention.attention.key.bias,
@@ -89,7 +104,7 @@ class DinoHandle:
             "ls1": lambda b: b.layer_scale1.lambda1, "n2_w": lambda b: b.norm2.weight, "n2_b": lambda b: b.norm2.bias,
             "fc1_w": lambda b: b.mlp.fc1.weight, "fc1_b": lambda b: b.mlp.fc1.bias,
             "fc2_w": lambda b: b.mlp.fc2.weight, "fc2_b": lambda b: b.mlp.fc2.bias, "ls2": lambda b: b.layer_scale2.lambda1,
-        }
+          }
         for name in _DINO_ARRAYS:
             ts = [get[name](b).detach().contiguous() for b in layers]
             arr = _ptr_array(ts)
@@ -100,7 +115,8 @@ class DinoHandle:
         if self.adapter_mlp is not None:
             w.adapter_fc1, w.adapter_fc2 = P(self.adapter_mlp.fc1.weight), P(self.adapter_mlp.fc2.weight)
             out_dim = self.adapter_mlp.fc2.weight.shape[0]
-        mode = 0 if self.adapter.condition_type in ("canny", "seg") else 1     # dinov2_adapter.py:20-24
+        # dinov2_adapter.py:20-24: nearest for canny / seg, bicubic otherwise; ViT_Adapter does not resize (nearest at P = 16 is the identity)
+        mode = 0 if (is_vit or self.adapter.condition_type in ("canny", "seg")) else 1
         d = CarDinoDesc(dtype=dtype_code(dt), hidden=m.hidden, heads=m.heads, layers=m.n_layers, patch=m.patch,
                         pos_grid=m.pos_grid, resize_mode=mode, adapter_out_dim=out_dim, eps=m.eps)
         if self.handle:

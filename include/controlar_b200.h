@@ -154,8 +154,8 @@ typedef struct CarDino CarDino;
 typedef struct CarDinoDesc {
     int32_t dtype;            /* dtype of the borrowed weights and of the input image (CAR_BF16 | CAR_F32) */
     int32_t hidden, heads, layers;
-    int32_t patch;            /* 14 */
-    int32_t pos_grid;         /* 37 (image_size 518 / 14) */
+    int32_t patch;            /* 14 (DINOv2) | 16 (HF ViT-S/16 of the legacy c2i class: unit LayerScale, resize_mode 0) */
+    int32_t pos_grid;         /* 37 (image_size 518 / 14) | 14 (224 / 16) */
     int32_t resize_mode;      /* 0 nearest (canny, seg) ; 1 bicubic align_corners=True (others) */
     int32_t adapter_out_dim;  /* d of adapter_mlp, 0 = no adapter_mlp registered */
     float   eps;              /* layer_norm_eps 1e-6 */
