@@ -33,3 +33,23 @@ def control_map(B: int, H: int, W: int, seed: int, kind: str, dtype=torch.float3
         lo = torch.rand(B, 1, max(H // 16, 1), max(W // 16, 1), generator=g)
         m = torch.nn.functional.interpolate(lo, size=(H, W), mode="bilinear", align_corners=False)
     return (2 * (m - 0.5)).repeat(1, 3, 1, 1).to(dtype)
+
+
+def train_attn_mask(emb_masks: torch.Tensor, n_img: int) -> torch.Tensor:
+    """Per-sample training mask of the t2i datasets, /root/reference/dataset/t2i_control.py:134-139 followed by the slicing of
+    train_t2i_canny.py:165-167: causal [S,S] with S = T + n_img, padded text COLUMNS switched off, diagonal forced on,
+    then [..., :-1, :-1].  Returns bool [B, 1, S-1, S-1]."""
+    B, T = emb_masks.shape
+    S = T + n_img
+    out = []
+    for b in range(B):
+        a = torch.tril(torch.ones(S, S))
+        a[:, :T] = a[:, :T] * emb_masks[b].float().unsqueeze(0)
+        eye = torch.eye(S)
+        out.append((a * (1 - eye) + eye).bool())
+    return torch.stack(out).unsqueeze(1)[:, :, :-1, :-1]
+
+
+def code_inputs(vocab: int, B: int, n_img: int, seed: int) -> torch.Tensor:
+    """VQ code grid z_indices [B, n_img] int64 (what dataset['code'] holds)."""
+    return torch.randint(0, vocab, (B, n_img), generator=torch.Generator().manual_seed(seed))

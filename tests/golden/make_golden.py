@@ -65,7 +65,7 @@ def fake_hf_cwd(adapter_size: str):
             os.chdir(old)
 
 
-def build_ref_gpt(spec: GPTSpec, seed: int, dtype):
+def build_ref_gpt(spec: GPTSpec, seed: int, dtype, **model_kw):
     from autoregressive.models.gpt_t2i import Transformer, ModelArgs
     with fake_hf_cwd(spec.adapter_size), contextlib.redirect_stdout(io.StringIO()):
         m = Transformer(ModelArgs(dim=spec.dim, n_layer=spec.n_layer, n_head=spec.n_head,
@@ -73,7 +73,7 @@ def build_ref_gpt(spec: GPTSpec, seed: int, dtype):
                                   cls_token_num=spec.cls_token_num, block_size=spec.block_size,
                                   caption_dim=spec.caption_dim, num_classes=spec.num_classes,
                                   model_type=spec.model_type, adapter_size=spec.adapter_size,
-                                  condition_type=spec.condition_type))
+                                  condition_type=spec.condition_type, **model_kw))
     sd = make_gpt_state_dict(spec, seed)
     ref_sd = m.state_dict()
     assert set(ref_sd.keys()) == set(sd.keys()), (set(ref_sd) ^ set(sd))
@@ -296,6 +296,62 @@ def gptpy_case():
     print("gptpy greedy", tuple(greedy.shape), "raw", tuple(raw.shape), flush=True)
 
 
+def train_case(name: str, spec: GPTSpec, B: int, H: int, W: int, autocast, use_mask: bool, valid, seed: int = 0,
+               drop_prob: float = 0.5, rand_seed: int = 1):
+    """the teacher-forced TRAINING forward (module in train mode, fp32 parameters, bf16 autocast like
+    train_t2i_canny.py:166-167 / train_c2i_canny.py:200-201) + backward through the reference, dropout layers at p = 0 and the
+    CFG drop decision recorded.  Stores logits, loss and a probe of every parameter gradient (oracle.train_oracle.grad_probe)."""
+    from oracle.inputs import train_attn_mask, code_inputs
+    from oracle.train_oracle import grad_probe
+    torch.set_grad_enabled(True)
+    m = build_ref_gpt(spec, seed, torch.float32, token_dropout_p=0.0, resid_dropout_p=0.0, ffn_dropout_p=0.0,
+                      class_dropout_prob=drop_prob)
+    m.train()
+    N = (H // 16) * (W // 16)
+    T = spec.cls_token_num
+    if spec.model_type == "t2i":
+        cond, masks = text_inputs(T, spec.caption_dim, B, seed + 1, torch.float32)
+    else:
+        cond, masks = class_inputs(spec.num_classes, B, seed + 1), None
+    cmap = control_map(B, H, W, seed + 2, "canny" if spec.condition_type in ("canny", "seg") else "depth", torch.float32)
+    z = code_inputs(spec.vocab_size, B, N, seed + 4)
+    mask = train_attn_mask(masks, N) if (use_mask and masks is not None) else None
+    vt = None if valid is None else torch.tensor(valid)
+    seen = {}
+    orig_drop = m.cls_embedding.token_drop
+
+    def spy_drop(*a, **k):
+        out = orig_drop(*a, **k)
+        seen["drop_ids"] = out[1].clone()
+        return out
+    m.cls_embedding.token_drop = spy_drop
+    hook = m.adapter.register_forward_hook(lambda mod, inp, out: (out.retain_grad(), seen.__setitem__("feat", out))[0])
+    torch.manual_seed(rand_seed)
+    ac = torch.autocast("cpu", dtype=autocast) if autocast is not None else contextlib.nullcontext()
+    kw = {} if mask is None else {"mask": mask}
+    if vt is not None:
+        kw["valid"] = vt
+    with ac, math_sdpa():
+        logits, loss = m(cond_idx=cond, idx=z[:, :-1], targets=z, condition=cmap if autocast is None else cmap.to(autocast), **kw)
+    loss.backward()
+    hook.remove()
+    grads = {k: grad_probe(k, p.grad) for k, p in m.named_parameters()
+             if p.grad is not None and not k.startswith("adapter.model.")}
+    no_grad = sorted(k for k, p in m.named_parameters() if p.grad is None)
+    small = {k: p.grad.clone() for k, p in m.named_parameters()
+             if p.grad is not None and (k.endswith("norm.weight") and ("layers.0." in k or k == "norm.weight"))}
+    out = {"header": header(), "spec": spec.__dict__, "seed": seed, "B": B, "H": H, "W": W,
+           "autocast": None if autocast is None else str(autocast), "sdpa": "math", "use_mask": bool(mask is not None),
+           "valid": valid, "dropout": "token/resid/ffn p = 0; class_dropout_prob = %g, torch.manual_seed(%d)" % (drop_prob, rand_seed),
+           "inputs": "oracle.inputs: text_inputs/class_inputs(seed+1), control_map(seed+2), code_inputs(seed+4), train_attn_mask",
+           "drop_ids": seen["drop_ids"], "feat": seen["feat"].detach().clone(), "feat_grad": seen["feat"].grad.clone(),
+           "logits": (logits.detach().to(autocast) if autocast is not None else logits.detach()).clone(),
+           "loss": loss.detach().clone(), "grads": grads, "grads_full": small, "params_without_grad": no_grad}
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    torch.set_grad_enabled(False)
+    print(name, "loss %.6f" % float(loss), "drop", seen["drop_ids"].tolist(), "grads", len(grads), flush=True)
+
+
 SMALL = dict(dim=256, n_layer=6, n_head=4, vocab_size=2048)
 
 CASES = {
@@ -332,6 +388,15 @@ CASES = {
     "dinov2": dino_case,
     "vit": vit_case,
     "c2i_gptpy_bf16": gptpy_case,
+    "train_t2i_small_ac": lambda: train_case("train_t2i_small_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
+                                             B=3, H=128, W=128, autocast=torch.bfloat16, use_mask=True, valid=[1, 0, 1]),
+    "train_t2i_small_fp32": lambda: train_case("train_t2i_small_fp32", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
+                                               B=3, H=128, W=128, autocast=None, use_mask=True, valid=[1, 1, 1]),
+    "train_c2i_small_ac": lambda: train_case("train_c2i_small_ac", GPTSpec(**SMALL, cls_token_num=1, block_size=64, model_type="c2i"),
+                                             B=4, H=128, W=128, autocast=torch.bfloat16, use_mask=False, valid=None),
+    "train_t2i_mr_ac": lambda: train_case("train_t2i_mr_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=144, model_type="t2i",
+                                                                     condition_type="depth"),
+                                          B=2, H=128, W=192, autocast=torch.bfloat16, use_mask=True, valid=[1, 1]),
 }
 
 if __name__ == "__main__":
