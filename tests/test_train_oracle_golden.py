@@ -101,3 +101,17 @@ def test_train_mask_and_valid_semantics():
     lg2, l2, _ = run(cond3, z)
     # image-token rows never see padded columns; their logits are unchanged
     assert torch.equal(lg0, lg2) and l0 == l2
+
+
+@pytest.mark.parametrize("shape", [(64, 96, 48, 80), (50, 70, 64, 64), (96, 96, 24, 40), (33, 47, 33, 100), (128, 128, 96, 160)])
+def test_resize_oracle_matches_torch(shape):
+    """Row f2 checker: oracle/resize_oracle.py against the call the reference makes (train_t2i_depth_multiscale.py:52-54),
+    `F.interpolate(..., mode='bilinear', align_corners=False, antialias=True)`, on 0..255 image data; fp32 summation-order noise only."""
+    import torch.nn.functional as F
+    from oracle.resize_oracle import bilinear_aa_resize
+    h, w, oh, ow = shape
+    x = torch.rand(2, 3, h, w, generator=torch.Generator().manual_seed(h * 1000 + w)) * 255
+    ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)
+    got = bilinear_aa_resize(x, (oh, ow))
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) < 1e-4           # 4e-7 of full scale
