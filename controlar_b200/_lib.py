@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcontrolar_b200.so")
+LIB_PATH = os.environ.get("CAR_LIB") or os.path.join(HERE, "lib", "libcontrolar_b200.so")   # CAR_LIB: dev A/B runs of another build
 
 CAR_BF16, CAR_F32 = 0, 1
 
@@ -50,6 +50,8 @@ PROTOTYPES = {
     "car_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(CarSampling), C.c_int32, C.c_int32,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "car_generate": (C.c_int, [C.c_void_p, C.POINTER(CarSampling), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "car_generate_forced": (C.c_int, [C.c_void_p, C.POINTER(CarSampling), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "car_decode_step_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
     "car_launch_count": (C.c_int64, [C.c_int32]),
     "car_op_linear": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -71,6 +73,8 @@ def lib():
                 "(controlar_b200 has no CPU / eager-PyTorch fallback)")
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
+            if os.environ.get("CAR_LIB") and not hasattr(l, name):
+                continue                                  # an older dev build may lack the newest entry points
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args

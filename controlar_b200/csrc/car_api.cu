@@ -11,6 +11,7 @@
 #include "sampler.cuh"
 #include "misc.cuh"
 #include "decode_persistent.cuh"
+#include "decode_pk2.cuh"
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
 #include <algorithm>
@@ -86,6 +87,11 @@ struct CarState {
     int pk_part_slots, pk_grid; bool pk_ok;
     unsigned int* pk_bar; unsigned int pk_bar_count, pk_tag_base;
     size_t pk_pkt_bytes; void* pk_pkt_base;
+    // two-chain persistent decode kernel (decode_pk2.cuh): per-micro-batch packet buffers
+    bool p2_ok; int p2_sms; int* p2_part; int p2_part_slots;
+    uint2 *p2_h2[P2_NMB][2], *p2_h1[P2_NMB][2], *p2_att[P2_NMB][2], *p2_act[P2_NMB][2], *p2_qkv[P2_NMB][2], *p2_partial[P2_NMB][2];
+    size_t p2_pkt_bytes; void* p2_pkt_base;
+    unsigned int* p2_bar; unsigned int p2_bar_count, p2_tag_base;
     std::vector<void*> owned;
 };
 
@@ -332,6 +338,50 @@ static int pk_state_setup(CarState* s) {
     return CAR_OK;
 }
 
+// two-chain kernel: block ownership per CTA rank (same balancing as pk_partition), packet buffers per micro-batch
+static int p2_state_setup(CarState* s) {
+    const CarModelDesc& d = s->m->d;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int G = sms, L = d.n_layer;
+    s->p2_sms = G;
+    std::vector<int> table;
+    pk_partition(d, G, table);
+    int maxq = 0, maxd = 0, maxp = 0, maxh = 0;
+    for (int c = 0; c < G; ++c) {
+        maxq = std::max(maxq, table[0 * (G + 1) + c + 1] - table[0 * (G + 1) + c]);
+        maxd = std::max(maxd, table[1 * (G + 1) + c + 1] - table[1 * (G + 1) + c]);
+        maxp = std::max(maxp, table[2 * (G + 1) + c + 1] - table[2 * (G + 1) + c]);
+        maxh = std::max(maxh, table[3 * (G + 1) + c + 1] - table[3 * (G + 1) + c]);
+    }
+    const int nbh = 8 * d.n_head;                       // pairs of a full micro-batch
+    s->p2_ok = s->b_eff <= 16 && d.dim % 256 == 0 && d.dim <= P2_KPW * P2_WARPS * 32 && d.ffn_dim % 256 == 0 &&
+               d.ffn_dim <= P2_MAXA * P2_WARPS * 32 && d.vocab_size % 4 == 0 && d.vocab_size <= 65536 && maxq <= P2_MAXBLK && maxd <= 2 && 2 * maxp <= P2_MAXBLK &&
+               maxh <= P2_MAXBLK && nbh <= 5 * G;
+    if (!s->p2_ok) return CAR_OK;
+    (void)L;
+    s->p2_part_slots = G / std::max(1, d.n_head) + 3;
+    if (getenv("CAR_TAG_EPOCH")) { static unsigned int epoch = 0; epoch += 0x00100000u; s->p2_tag_base = epoch; }   // dev: unique tags per state   // a pair of the smallest micro-batch (1 row) can span G / H CTAs
+    const size_t a_d = (size_t)(d.dim / 32) * 1024, a_f = (size_t)(d.ffn_dim / 32) * 1024;
+    const size_t qkv_b = (size_t)3 * 8 * d.n_head * 8 * 4 * 8, part_b = (size_t)nbh * s->p2_part_slots * 66 * 8;
+    const size_t per = 2 * (3 * a_d + a_f + qkv_b + part_b);
+    CAR_TRY(alloc_dev(s->owned, (void**)&s->p2_part, table.size() * sizeof(int)));
+    CAR_TRY(alloc_dev(s->owned, (void**)&s->p2_bar, 64));
+    CAR_TRY(alloc_dev(s->owned, &s->p2_pkt_base, P2_NMB * per));
+    s->p2_pkt_bytes = P2_NMB * per;
+    unsigned char* q = (unsigned char*)s->p2_pkt_base;
+    for (int mb = 0; mb < P2_NMB; ++mb)
+        for (int par = 0; par < 2; ++par) {
+            s->p2_h2[mb][par] = (uint2*)q; q += a_d; s->p2_h1[mb][par] = (uint2*)q; q += a_d; s->p2_att[mb][par] = (uint2*)q; q += a_d;
+            s->p2_act[mb][par] = (uint2*)q; q += a_f; s->p2_qkv[mb][par] = (uint2*)q; q += qkv_b; s->p2_partial[mb][par] = (uint2*)q; q += part_b;
+        }
+    CAR_CUDA(cudaMemcpy(s->p2_part, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CAR_CUDA(cudaMemset(s->p2_bar, 0, 64));
+    CAR_CUDA(cudaMemset(s->p2_pkt_base, 0, s->p2_pkt_bytes));
+    return CAR_OK;
+}
+
 extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N, void* const* k_cache, void* const* v_cache,
                                 const float* rope_table, CarState** out) {
     if (!m || !k_cache || !v_cache || !rope_table || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
@@ -370,8 +420,10 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     // persistent decode kernel resources (bf16 only)
     s->pk_ptrs = nullptr; s->pk_part = nullptr; s->pk_bar = nullptr; s->pk_grid = 0; s->pk_ok = false;
     s->pk_bar_count = 0; s->pk_tag_base = 0; s->pk_pkt_base = nullptr; s->pk_pkt_bytes = 0;
+    s->p2_ok = false; s->p2_part = nullptr; s->p2_bar = nullptr; s->p2_bar_count = 0; s->p2_tag_base = 0; s->p2_pkt_base = nullptr; s->p2_pkt_bytes = 0;
     if (d.dtype == CAR_BF16) {
         int r2 = pk_state_setup(s);
+        if (r2 == CAR_OK) r2 = p2_state_setup(s);
         if (r2 != CAR_OK) { for (void* p : s->owned) cudaFree(p); delete s; return r2; }
     }
     s->emb_mask_store = s->emb_mask;
@@ -688,7 +740,7 @@ static int loop_sample_args(CarState* s, const CarSampling* sp, const float* noi
 }
 
 // the whole decode loop as one persistent cooperative kernel (decode_persistent.cuh)
-static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st) {
+static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st, const int32_t* forced = nullptr, float* trace = nullptr) {
     const CarModelDesc& d = s->m->d;
     const int L = d.n_layer;
     if (s->pk_tag_base > 0x7fff0000u) {   // tag wrap: restart the epoch counter on zeroed packets
@@ -713,6 +765,8 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
     }
     P.part_slots = s->pk_part_slots; P.tag_base = s->pk_tag_base; P.bar = s->pk_bar; P.bar_base = s->pk_bar_count;
     P.smp = a; P.n_steps = n_tokens;
+    P.forced = forced; P.forced_ld = n_tokens; P.trace = trace;
+    if (trace) CAR_CUDA(cudaMemcpyAsync(trace, s->logits, (size_t)s->b_eff * d.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
     { const char* e = getenv("CAR_EXP"); P.exp_flags = e ? atoi(e) : 0; }
     static bool attr_set = false;
     if (!attr_set) {
@@ -783,6 +837,110 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
     return CAR_OK;
 }
 
+// the two-chain persistent kernel (decode_pk2.cuh): 2 CTAs of 256 threads per SM, one per micro-batch
+static int launch_pk2(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st, const int32_t* forced, float* trace) {
+    const CarModelDesc& d = s->m->d;
+    const int L = d.n_layer;
+    if (s->p2_tag_base > 0x7fff0000u) {
+        CAR_CUDA(cudaMemsetAsync(s->p2_pkt_base, 0, s->p2_pkt_bytes, st));
+        s->p2_tag_base = 0;
+    }
+    P2Params P;
+    memset(&P, 0, sizeof(P));
+    P.dim = d.dim; P.F = d.ffn_dim; P.V = d.vocab_size; P.L = L; P.H = d.n_head; P.T = s->T; P.S = s->S; P.n_img = s->N;
+    P.b_eff = s->b_eff; P.B = a.B; P.eps = d.norm_eps; P.cs = s->cs;
+    // micro-batches: images split in two halves (the first takes the odd one); a single image runs one chain
+    P.nmb = a.B >= 2 ? 2 : 1;
+    P.img_lo[0] = 0; P.img_cnt[0] = (a.B + P.nmb - 1) / P.nmb;
+    P.img_lo[1] = P.img_cnt[0]; P.img_cnt[1] = a.B - P.img_cnt[0];
+    if (P.img_cnt[0] * (a.use_cfg ? 2 : 1) > 8) CAR_FAIL(CAR_ERR_UNSUPPORTED, "more than 8 rows per micro-batch");
+    P.tok_emb = (const bf16*)s->m->tok_emb; P.norm_w = (const bf16*)s->m->norm; P.w_out = (const uint4*)s->m->g_output;
+    void** pp = s->pk_ptrs;
+    P.wqkv = (const uint4* const*)(pp + 0 * L); P.wo = (const uint4* const*)(pp + 1 * L); P.w13 = (const uint4* const*)(pp + 2 * L);
+    P.w2 = (const uint4* const*)(pp + 3 * L); P.attn_norm = (const bf16* const*)(pp + 4 * L); P.ffn_norm = (const bf16* const*)(pp + 5 * L);
+    P.kc = (bf16* const*)(pp + 6 * L); P.vc = (bf16* const*)(pp + 7 * L);
+    for (int j = 0; j < 3; ++j) P.ctrl[j] = (const bf16*)s->ctrl[j];
+    P.has_ctrl = s->has_ctrl ? 1 : 0;
+    P.rope = s->rope; P.emb_mask = s->emb_mask; P.logits = s->logits; P.part = s->p2_part;
+    for (int mb = 0; mb < P2_NMB; ++mb)
+        for (int par = 0; par < 2; ++par) {
+            P.h2[mb][par] = s->p2_h2[mb][par]; P.h1[mb][par] = s->p2_h1[mb][par]; P.att[mb][par] = s->p2_att[mb][par];
+            P.act[mb][par] = s->p2_act[mb][par]; P.qkv[mb][par] = s->p2_qkv[mb][par]; P.partial[mb][par] = s->p2_partial[mb][par];
+        }
+    P.part_slots = s->p2_part_slots; P.tag_base = s->p2_tag_base; P.bar = s->p2_bar; P.bar_base = s->p2_bar_count;
+    P.smp = a; P.n_steps = n_tokens;
+    P.forced = forced; P.forced_ld = n_tokens; P.trace = trace;
+    if (trace) CAR_CUDA(cudaMemcpyAsync(trace, s->logits, (size_t)s->b_eff * d.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
+    { const char* e = getenv("CAR_EXP"); P.exp_flags = e ? atoi(e) : 0; }
+    CAR_CUDA(cudaFuncSetAttribute(pk2_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_TOTAL));
+    int occ = 0;
+    CAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk2_decode_kernel, P2_THREADS, P2_SMEM_TOTAL));
+    if (occ < P.nmb) CAR_FAIL(CAR_ERR_UNSUPPORTED, "two-chain decode kernel: fewer than 2 CTAs fit on an SM");
+    const int grid = P.nmb * s->p2_sms;
+    static long long* mdbg = nullptr;
+    static int* nanflag = nullptr;
+    const size_t nf_n = (size_t)2 * 8 * (L + 1) * 16;
+    const size_t dbg_n = (size_t)grid * 64;
+    if (getenv("CAR_NANCHK")) {
+        if (!nanflag) cudaMalloc(&nanflag, 2 * 8 * 64 * 16 * 4);
+        cudaMemsetAsync(nanflag, 0, nf_n * 4, st);
+        P.nanflag = nanflag;
+    }
+    if (tune().dbg) {
+        if (!mdbg) { cudaMalloc(&mdbg, 2 * 148 * 64 * 8 * 2); }
+        cudaMemsetAsync(mdbg, 0, dbg_n * 8, st);
+        P.dbg = mdbg; P.dbg_step = std::max(0, std::min(n_tokens - 2, tune().dbg));
+    }
+    void* args[] = {&P};
+    CAR_CUDA(cudaLaunchCooperativeKernel((const void*)pk2_decode_kernel, dim3(grid), dim3(P2_THREADS), args, P2_SMEM_TOTAL, st));
+    s->p2_bar_count += (unsigned int)(n_tokens - 1) * (unsigned int)grid;
+    s->p2_tag_base += (unsigned int)(n_tokens - 1) * (unsigned int)(L + 1);
+    g_car_launches.fetch_add(1, std::memory_order_relaxed);
+    if (P.nanflag) {
+        cudaStreamSynchronize(st);
+        std::vector<int> f(nf_n);
+        cudaMemcpy(f.data(), nanflag, nf_n * 4, cudaMemcpyDeviceToHost);
+        int shown = 0;
+        for (int mbi = 0; mbi < 2; ++mbi)
+            for (int sI = 0; sI < 8 && shown < 12; ++sI)
+                for (int l = 0; l <= L && shown < 12; ++l)
+                    for (int k = 0; k < 16; ++k)
+                        if (f[((mbi * 8 + sI) * (L + 1) + l) * 16 + k]) { fprintf(stderr, "[pk2 nan] mb %d step %d layer %d site %d\n", mbi, sI, l, k); ++shown; }
+        if (!shown) fprintf(stderr, "[pk2 nan] none\n");
+    }
+    if (tune().dbg) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> t(dbg_n);
+        cudaMemcpy(t.data(), mdbg, dbg_n * 8, cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (int c = 0; c < grid; ++c) if (t[(size_t)c * 64] && (!t0 || t[(size_t)c * 64] < t0)) t0 = t[(size_t)c * 64];
+        auto stat = [&](int slot, const char* name) {
+            for (int mbi = 0; mbi < P.nmb; ++mbi) {
+                std::vector<long long> v;
+                for (int c = mbi; c < grid; c += P.nmb) if (t[(size_t)c * 64 + slot]) v.push_back(t[(size_t)c * 64 + slot] - t0);
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, "[pk2 mb%d] %-22s n=%3zu  min %8.2f  med %8.2f  max %8.2f us\n", mbi, name, v.size(), v.front() * 1e-3, v[v.size() / 2] * 1e-3, v.back() * 1e-3);
+            }
+        };
+        if (!t0) fprintf(stderr, "[pk2] no stamps: rebuild with CAR_PK_TRACE=1 (python -m controlar_b200.build --force)\n");
+        fprintf(stderr, "[pk2] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
+        stat(0, "step start"); stat(1, "sampler done");
+        const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
+        for (int k = 0; k < 5; ++k) {
+            char buf[64];
+            const char* sub[5] = {"start", k == 1 ? "q polled" : "A polled", k == 1 ? "keys done" : "normed", k == 1 ? "end" : "mma done", "end"};
+            for (int j = 0; j < (k == 1 ? 4 : 5); ++j) { snprintf(buf, sizeof buf, "L3 %s %s", nm[k], sub[j]); stat(8 + 8 * k + j, buf); }
+        }
+        stat(3, "head done"); stat(4, "barrier passed");
+    }
+    return CAR_OK;
+}
+static bool use_pk2(const CarState* s) {
+    static const int sel = [] { const char* e = getenv("CAR_PK"); return e ? atoi(e) : 1; }();     // dev: CAR_PK=2 -> experimental two-chain kernel (decode_pk2.cuh; measured slower, see profiles/r2_two_chain_experiment.md)
+    return sel == 2 && s->p2_ok;
+}
+
 extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise, int32_t* tokens_out,
                             void* stream) {
     if (!s || !sp || !tokens_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
@@ -792,7 +950,8 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
     SampleArgs a;
     CAR_TRY(loop_sample_args(s, sp, noise, a));
     if (s->m->d.dtype == CAR_BF16 && tune().mega && s->pk_ok) {
-        CAR_TRY(launch_pk(s, a, n_tokens, st));
+        if (use_pk2(s)) CAR_TRY(launch_pk2(s, a, n_tokens, st, nullptr, nullptr));
+        else CAR_TRY(launch_pk(s, a, n_tokens, st));
         CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, a.B,
                                    cudaMemcpyDeviceToDevice, st));
         CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1 + n_tokens);
@@ -837,6 +996,28 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
                     t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[5] - t[0]);
         }
     }
+    return CAR_OK;
+}
+
+// teacher-forced run of the SAME device-side loop (parity tests): the token fed to step i + 1 is forced[b][i]; the sampler still
+// runs and tokens_out holds what it would have chosen at every step given the forced prefix; logits_trace (optional) receives the
+// raw model logits of every step.
+extern "C" int car_generate_forced(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise, const int32_t* forced_tokens,
+                                   float* logits_trace, int32_t* tokens_out, void* stream) {
+    if (!s || !sp || !tokens_out || !forced_tokens) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (!s->prefilled) CAR_FAIL(CAR_ERR_STATE, "car_generate_forced must follow car_prefill on the same state");
+    if (n_tokens < 1 || n_tokens > s->N) CAR_FAIL(CAR_ERR_ARG, "n_tokens must be in [1, N]");
+    if (!(s->m->d.dtype == CAR_BF16 && s->pk_ok))
+        CAR_FAIL(CAR_ERR_UNSUPPORTED, "teacher forcing through the device-side loop needs the persistent decode kernel (bf16); use car_decode_step");
+    cudaStream_t st = (cudaStream_t)stream;
+    SampleArgs a;
+    CAR_TRY(loop_sample_args(s, sp, noise, a));
+    if (use_pk2(s)) CAR_TRY(launch_pk2(s, a, n_tokens, st, forced_tokens, logits_trace));
+    else CAR_TRY(launch_pk(s, a, n_tokens, st, forced_tokens, logits_trace));
+    CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, a.B,
+                               cudaMemcpyDeviceToDevice, st));
+    CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1 + n_tokens);
+    s->prefilled = false;
     return CAR_OK;
 }
 

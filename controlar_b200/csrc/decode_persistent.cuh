@@ -55,6 +55,8 @@ struct PkParams {
     unsigned int* bar; unsigned int bar_base;
     SampleArgs smp;
     int n_steps;                       // tokens to produce (decode iterations = n_steps - 1)
+    const int* forced; int forced_ld;  // teacher forcing (parity tests): token fed to the next step = forced[b * forced_ld + step] instead of the sampled one
+    float* trace;                      // optional [n_steps][b_eff][V] fp32: raw model logits of every step (trace[0] = prefill logits, copied by the host)
     int exp_flags;                     // dev experiments (CAR_EXP)
     long long* dbg; int dbg_step;      // dev instrumentation: [grid][64] globaltimer stamps (ns) of one step / layer 3
 };
@@ -281,7 +283,8 @@ __device__ __forceinline__ const bf16* pk_ctrl_next(const PkParams& P, int l) {
 }
 
 __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& sm, const int kind, const int l, const int pos,
-                                              const unsigned int tag, int blk_lo, int blk_hi, unsigned int& cons, long long* dbg, long long* wdbg_base) {
+                                              const unsigned int tag, int blk_lo, int blk_hi, unsigned int& cons, long long* dbg, long long* wdbg_base,
+                                              float* trace_rows = nullptr) {
     const int par = l & 1;
     const bool NORM = (kind == 0 || kind == 2 || kind == 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -540,6 +543,10 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                     // logits = output(norm(h)).float()  gpt_t2i.py:469-470 (bf16 head output, then fp32)
                     if (r_lo < M) *reinterpret_cast<float2*>(P.logits + (size_t)r_lo * P.V + n) = make_float2(rnd<bf16>(v00), rnd<bf16>(v01));
                     if (r_hi < M) *reinterpret_cast<float2*>(P.logits + (size_t)r_hi * P.V + n) = make_float2(rnd<bf16>(v10), rnd<bf16>(v11));
+                    if (trace_rows != nullptr) {
+                        if (r_lo < M) *reinterpret_cast<float2*>(trace_rows + (size_t)r_lo * P.V + n) = make_float2(rnd<bf16>(v00), rnd<bf16>(v01));
+                        if (r_hi < M) *reinterpret_cast<float2*>(trace_rows + (size_t)r_hi * P.V + n) = make_float2(rnd<bf16>(v10), rnd<bf16>(v11));
+                    }
                 }
             }
         }
@@ -897,7 +904,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
             a.h_out = nullptr; a.tok_buf = nullptr;
             sample_body<PK_THREADS, 32>(a, blockIdx.x);
             __syncthreads();
-            if (tid == 0) s_tok = ld_cg(a.idx_out + (size_t)blockIdx.x * a.tokens_ld + step);
+            if (tid == 0) s_tok = P.forced != nullptr ? __ldg(P.forced + (size_t)blockIdx.x * P.forced_ld + step)
+                                                      : ld_cg(a.idx_out + (size_t)blockIdx.x * a.tokens_ld + step);
             __syncthreads();
             if (step + 1 < P.n_steps) {
                 const int tok = s_tok;
@@ -919,7 +927,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
                 if (l < P.L && ph == 1) { pk_attn_phase(P, sm, l, p, tag, par, dbg); continue; }
                 const int kind = l == P.L ? 4 : (ph == 0 ? 0 : ph - 1);
                 pk_gemm_phase(P, sm, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg,
-                              (dbg != nullptr && (int)blockIdx.x == 77 % (int)gridDim.x) ? P.dbg + (size_t)gridDim.x * 64 + (size_t)ph * 256 : nullptr);
+                              (dbg != nullptr && (int)blockIdx.x == 77 % (int)gridDim.x) ? P.dbg + (size_t)gridDim.x * 64 + (size_t)ph * 256 : nullptr,
+                              (kind == 4 && P.trace != nullptr) ? P.trace + (size_t)(step + 1) * P.b_eff * P.V : nullptr);
             }
         }
         if (dbg_step && tid == 0) dbg_cta[3] = pk_now();

@@ -163,6 +163,22 @@ class ARStateHandle:
         self._noise_keep = noise
         return out
 
+    def generate_forced(self, sp: CarSampling, forced: torch.Tensor, trace: bool = True, noise: Optional[torch.Tensor] = None):
+        """Teacher-forced device-side loop (car_generate_forced): returns (sampler choices int32 [B, n], logits fp32 [n, b_eff, V])."""
+        B = self.b_eff // 2 if sp.cfg_scale > 1.0 else self.b_eff
+        forced = forced.to(torch.int32).contiguous()
+        assert forced.shape[0] == B, forced.shape
+        n = forced.shape[1]
+        out = torch.empty((B, n), dtype=torch.int32, device=forced.device)
+        tr = torch.empty((n, self.b_eff, self.V), dtype=torch.float32, device=forced.device) if trace else None
+        if noise is not None:
+            noise = noise.to(torch.float32).contiguous()
+            assert noise.shape == (n, B, self.V), noise.shape
+        check(self.lib.car_generate_forced(self.handle, C.byref(sp), int(n), _ptr(noise), _ptr(forced), _ptr(tr), _ptr(out),
+                                           cur_stream()), "car_generate_forced")
+        self._noise_keep = (noise, forced)
+        return out, tr
+
     def step_bytes(self, n_context: int) -> int:
         return int(self.lib.car_decode_step_bytes(self.handle, int(n_context)))
 

@@ -132,6 +132,14 @@ int car_sample(const float* logits, int32_t b_eff, int32_t V, const CarSampling*
 int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise,
                  int32_t* tokens_out, void* stream);
 
+/* Teacher-forced run of the same device-side loop (parity instrumentation; the reference equivalent is calling
+ * Transformer.forward(idx=forced[:, i], input_pos=[T+i]) step by step, gpt_t2i.py:444-470 / generate.py:97-110).
+ * forced_tokens int32 [B, n_tokens] (device): the token fed to step i+1 is forced[b][i]; the sampler still runs and
+ * tokens_out[b][i] is its choice given the forced prefix.  logits_trace (optional, device) fp32 [n_tokens, b_eff, V]
+ * receives the raw model logits of every step (row 0 = the prefill logits).  bf16 persistent kernel only. */
+int car_generate_forced(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise,
+                        const int32_t* forced_tokens, float* logits_trace, int32_t* tokens_out, void* stream);
+
 /* Algorithmic HBM bytes of one decode step at context length n (SURVEY.md §8d formula). */
 int64_t car_decode_step_bytes(const CarState* s, int32_t n_context);
 /* Number of kernels the library launched since the counter was last reset (bench.py "gpu_launches"). */

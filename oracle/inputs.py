@@ -35,6 +35,13 @@ def control_map(B: int, H: int, W: int, seed: int, kind: str, dtype=torch.float3
     return (2 * (m - 0.5)).repeat(1, 3, 1, 1).to(dtype)
 
 
+def xl_ctrl_in(B: int, N: int, dim: int, seed: int, dtype=torch.float32):
+    """Procedural adapter_mlp output [B, N, dim] for the XL-shape teacher-forced fixtures (never stored; the control encoder has
+    its own goldens)."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, N, dim, generator=g) * 0.5).to(dtype)
+
+
 def train_attn_mask(emb_masks: torch.Tensor, n_img: int) -> torch.Tensor:
     """Per-sample training mask of the t2i datasets, /root/reference/dataset/t2i_control.py:134-139 followed by the slicing of
     train_t2i_canny.py:165-167: causal [S,S] with S = T + n_img, padded text COLUMNS switched off, diagonal forced on,

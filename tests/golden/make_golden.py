@@ -26,7 +26,7 @@ import torch
 import transformers
 
 from oracle.weights import GPTSpec, make_gpt_state_dict, make_vq_state_dict, gpt_shapes, vq_shapes
-from oracle.inputs import text_inputs, class_inputs, control_map
+from oracle.inputs import text_inputs, class_inputs, control_map, xl_ctrl_in
 
 torch.set_grad_enabled(False)
 
@@ -352,6 +352,84 @@ def train_case(name: str, spec: GPTSpec, B: int, H: int, W: int, autocast, use_m
     print(name, "loss %.6f" % float(loss), "drop", seen["drop_ids"].tolist(), "grads", len(grads), flush=True)
 
 
+XL = dict(dim=1280, n_layer=36, n_head=20, vocab_size=16384)
+
+
+def xl_forced_case(name: str, B: int, n_tokens: int, full_steps, col_stride_after: int = 8, seed: int = 0,
+                   cfg_scale: float = 4.0, cs: float = 0.6, threads: int = 0):
+    """the reference's generate() at GPT-XL shape (dim 1280 / H 20 / F 3584 / V 16384 / L 36, block_size 1024,
+    T 120) in bf16 with CFG, left-padded masks and control_strength != 1, TEACHER-FORCED along a fixed random token grid:
+    generate.py's `sample` is replaced by a function that returns the forced token, every other line of generate()/prefill/
+    decode_one_token/Transformer.forward runs unmodified.  Stored (bf16-exact, the reference's logits are bf16 values):
+    full logits rows at `full_steps`, a 256-column probe at every step < 64 and every `col_stride_after`-th step after, and per
+    step the CFG-combined arg-max + top-2 margin + |logit| max."""
+    import autoregressive.models.generate as G
+    if threads:
+        torch.set_num_threads(threads)
+    dtype = torch.bfloat16
+    spec = GPTSpec(**XL, cls_token_num=120, block_size=1024, model_type="t2i")
+    m = build_ref_gpt(spec, seed, dtype)
+    m.adapter = torch.nn.Identity()          # generate.py:137-138 then pass the procedural control tokens through
+    m.adapter_mlp = torch.nn.Identity()
+    N_img = 1024
+    cond, masks = text_inputs(spec.cls_token_num, spec.caption_dim, B, seed + 1, dtype)
+    ctrl_in = xl_ctrl_in(B, N_img, spec.dim, seed + 7, dtype)
+    g = torch.Generator().manual_seed(seed + 11)
+    forced = torch.randint(0, spec.vocab_size, (B, n_tokens), generator=g, dtype=torch.int64)
+    cols = torch.randperm(spec.vocab_size, generator=g)[:256].sort().values
+    full_steps = [s for s in full_steps if s < n_tokens]
+    col_steps = [s for s in range(n_tokens) if s < 64 or s % col_stride_after == 0 or s == n_tokens - 1]
+    rec = {"full": {}, "cols": {}, "argmax": [], "margin": [], "absmax": []}
+    state = {"i": 0}
+    orig_forward = m.forward
+
+    def spy(*a, **k):
+        lg, loss = orig_forward(*a, **k)
+        raw = lg[:, -1].float()                       # [B_eff, V] fp32 carrier of bf16 values (gpt_t2i.py:470)
+        i = state["i"]
+        if i in full_steps:
+            rec["full"][i] = raw.to(dtype).clone()
+        if i in col_steps:
+            rec["cols"][i] = raw[:, cols].to(dtype).clone()
+        c, u = raw[:B], raw[B:]
+        z = u + (c - u) * cfg_scale
+        t2 = torch.topk(z, 2, dim=-1)
+        rec["argmax"].append(t2.indices[:, 0].clone())
+        rec["margin"].append((t2.values[:, 0] - t2.values[:, 1]).clone())
+        rec["absmax"].append(raw.abs().max().clone())
+        return lg, loss
+
+    def forced_sample(logits, **kw):
+        i = state["i"]
+        state["i"] = i + 1
+        if i % 32 == 0:
+            print(f"  {name}: step {i}/{n_tokens}", flush=True)
+        return forced[:, i:i + 1].clone(), torch.zeros(1)
+
+    m.forward = spy
+    orig_sample = G.sample
+    G.sample = forced_sample
+    try:
+        with math_sdpa():
+            out_tokens = G.generate(m, cond, n_tokens, emb_masks=masks, cfg_scale=cfg_scale, condition=ctrl_in,
+                                    control_strength=cs, temperature=1.0, top_k=0, top_p=1.0, sample_logits=False)
+    finally:
+        G.sample = orig_sample
+        m.forward = orig_forward
+    assert torch.equal(out_tokens.long(), forced)
+    out = {"header": header(), "spec": spec.__dict__, "seed": seed, "dtype": str(dtype), "B": B, "n_tokens": n_tokens,
+           "N_img": N_img, "cfg_scale": cfg_scale, "control_strength": cs, "prefill_sdpa": "math",
+           "inputs": "oracle.inputs.text_inputs(seed+1); ctrl_in = randn(B,1024,1280, seed+7)*0.5 (bf16) fed as adapter_mlp output; "
+                     "forced tokens randint(seed+11)",
+           "emb_masks": masks, "forced_tokens": forced.to(torch.int32), "cols": cols,
+           "full_steps": full_steps, "full_logits": torch.stack([rec["full"][s] for s in full_steps], dim=1),
+           "col_steps": col_steps, "col_logits": torch.stack([rec["cols"][s] for s in col_steps], dim=1),
+           "argmax_cfg": torch.stack(rec["argmax"], dim=1).to(torch.int32), "margin_cfg": torch.stack(rec["margin"], dim=1),
+           "raw_absmax": torch.stack(rec["absmax"])}
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    print(name, "done", tuple(out["full_logits"].shape), tuple(out["col_logits"].shape), flush=True)
+
+
 SMALL = dict(dim=256, n_layer=6, n_head=4, vocab_size=2048)
 
 CASES = {
@@ -394,12 +472,15 @@ CASES = {
                                                B=3, H=128, W=128, autocast=None, use_mask=True, valid=[1, 1, 1]),
     "train_c2i_small_ac": lambda: train_case("train_c2i_small_ac", GPTSpec(**SMALL, cls_token_num=1, block_size=64, model_type="c2i"),
                                              B=4, H=128, W=128, autocast=torch.bfloat16, use_mask=False, valid=None),
+    "xl_b1_long": lambda: xl_forced_case("xl_b1_long", B=1, n_tokens=1024, full_steps=(0, 1, 2, 391, 392, 777, 1022, 1023)),
+    "xl_b8_short": lambda: xl_forced_case("xl_b8_short", B=8, n_tokens=49, full_steps=(0, 1, 2, 7, 23, 48)),
+    "xl_b8_long": lambda: xl_forced_case("xl_b8_long", B=8, n_tokens=1024, full_steps=(0, 1, 65, 391, 1023)),
     "train_t2i_mr_ac": lambda: train_case("train_t2i_mr_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=144, model_type="t2i",
                                                                      condition_type="depth"),
                                           B=2, H=128, W=192, autocast=torch.bfloat16, use_mask=True, valid=[1, 1]),
 }
 
 if __name__ == "__main__":
-    todo = sys.argv[1:] or list(CASES)
+    todo = sys.argv[1:] or [c for c in CASES if not c.startswith('xl_')]   # XL cases: minutes to ~40 min of CPU, on request
     for c in todo:
         CASES[c]()

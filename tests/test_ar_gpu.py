@@ -83,6 +83,45 @@ def test_teacher_forced_logits_vs_golden_and_oracle(name):
         assert rate < 0.25, f"{name}: {rate:.3f} of teacher-forced arg-maxes differ"
 
 
+@pytest.mark.parametrize("name", ["t2i_small_bf16", "c2i_small_bf16", "t2i_mr_bf16", "t2i_mr_tall_bf16"])
+def test_persistent_kernel_teacher_forced_every_step(name):
+    """The PRODUCT bf16 decode path (the persistent kernel behind car_generate), teacher-forced along the reference's greedy
+    trajectory through car_generate_forced: raw logits of EVERY step vs the reference golden (not only up to the first
+    divergence of a free-running comparison)."""
+    import json, os
+    from controlar_b200 import engine
+    g, spec, dt, model, sd, cond, masks = _setup(name)
+    dev = "cuda"
+    B, N, T = g["B"], g["greedy_tokens"].shape[1], spec.cls_token_num
+    use_cfg = g["cfg_scale"] > 1.0
+    b_eff = 2 * B if use_cfg else B
+    ctrl_in = g["ctrl_in"].to(dev)
+    c = cond.to(dev)
+    if spec.model_type == "t2i":
+        cc = torch.cat([c, torch.zeros_like(c) + model.cls_embedding.uncond_embedding]) if use_cfg else c
+    else:
+        cc = torch.cat([c, torch.full_like(c, spec.num_classes)]) if use_cfg else c
+    cond_comb = torch.cat([ctrl_in, torch.zeros_like(ctrl_in)]) if use_cfg else ctrl_in
+    model.setup_caches(b_eff, T + N, dt, n_img_tokens=N)
+    st = model._car_state
+    st.set_emb_mask(None if masks is None else (torch.cat([masks, masks]).to(dev) if use_cfg else masks.to(dev)))
+    cs = g["control_strength"] if use_cfg else 1.0
+    st.prefill(cc, cond_comb, cs, all_rows=False)
+    sp = engine.make_sampling(temperature=1.0, top_k=0, top_p=1.0, sample_logits=False, cfg_scale=g["cfg_scale"])
+    choice, trace = st.generate_forced(sp, g["greedy_tokens"].to(dev))
+    got = trace.permute(1, 0, 2).float().cpu()          # [b_eff, N, V]
+    assert bool(torch.isfinite(got).all()), f"{name}: non-finite logits at steps {sorted(set((~torch.isfinite(got)).nonzero()[:, 1].tolist()))[:8]}"
+    ref_all = g["raw_logits_all"].float()
+    worst = max(rel_l2(got[:, i], ref_all[:, i]) for i in range(N))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "small_parity.jsonl"), "a") as fh:
+        fh.write(json.dumps({"case": name, "worst_step_rel_l2": worst}) + "\n")
+    assert worst < TOL[dt], f"{name}: worst per-step rel-L2 vs reference golden {worst:.3e}"
+    zr = cfg_combine(ref_all, g["cfg_scale"]) if use_cfg else ref_all
+    rate = assert_mismatches_are_near_ties(zr, ref_all, g["greedy_tokens"].long(), choice.cpu().long(), g["cfg_scale"], name)
+    assert rate < 0.25, f"{name}: {rate:.3f} of teacher-forced choices differ"
+
+
 @pytest.mark.parametrize("name", ["t2i_small_fp32", "c2i_small_fp32"])
 def test_generate_greedy_bit_exact_fp32(name):
     """Free-running device-side loop (car_prefill + car_generate): greedy token grid == reference golden."""
