@@ -45,6 +45,7 @@ PROTOTYPES = {
                                    C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]),
     "car_state_set_emb_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "car_state_destroy": (C.c_int, [C.c_void_p]),
+    "car_state_set_step_timer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "car_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "car_decode_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "car_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(CarSampling), C.c_int32, C.c_int32,
@@ -97,9 +98,18 @@ def dtype_code(dt) -> int:
     raise RuntimeError(f"controlar_b200 supports bf16 and fp32 checkpoints, not {dt}")
 
 
-def cur_stream() -> int:
+def cur_stream(device=None) -> int:
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t):
+    """Context manager that makes the device of tensor `t` current for the duration of a library call: the library launches on
+    the current device and takes the stream from it (the reference wraps its calls in `with torch.device(device)`,
+    generate.py:179-182)."""
+    import torch
+    return torch.cuda.device(t.device)
 
 
 def _ptr(t):

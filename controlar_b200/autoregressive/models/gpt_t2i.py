@@ -230,7 +230,7 @@ class Transformer(nn.Module):
         key = (max_batch_size, S, n_img, dtype, str(dev))
         mh = self._model_handle()
         if self._car_state is not None and getattr(self, "_state_key", None) == key and self._car_state.model is mh \
-                and self._car_state.model.handle.value == self._state_model_id:
+                and mh.generation == self._state_model_id:
             # same shapes: reuse caches, scratch and the captured decode graph.  (The reference re-allocates zeroed
             # caches on every call; slots beyond the current position are never read, so stale contents are inert.)
             self.causal_mask = torch.tril(torch.ones(S, S, dtype=torch.bool, device=dev)).unsqueeze(0).repeat(max_batch_size, 1, 1)
@@ -250,7 +250,7 @@ class Transformer(nn.Module):
             [b.attention.kv_cache.k_cache for b in self.layers], [b.attention.kv_cache.v_cache for b in self.layers],
             self.freqs_cis.contiguous())
         self._state_key = key
-        self._state_model_id = mh.handle.value
+        self._state_model_id = mh.generation
         self._mask_synced = False
 
     def _sync_mask(self):

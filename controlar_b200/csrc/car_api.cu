@@ -11,7 +11,6 @@
 #include "sampler.cuh"
 #include "misc.cuh"
 #include "decode_persistent.cuh"
-#include "decode_pk2.cuh"
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
 #include <algorithm>
@@ -49,6 +48,7 @@ struct CarModel {
     // owned GEMM-ready copies: bf16 -> fragment-packed; fp32 -> plain (only w13 is an owned interleaved copy)
     std::vector<void*> g_wqkv, g_wo, g_w13, g_w2;
     void *g_output, *g_cap_fc1, *g_cap_fc2, *g_cond_fc1, *g_cond_fc2, *g_ctl_fc1[3], *g_ctl_fc2[3];
+    unsigned int pack_gen = 0;       // bumped by every (re)pack: states refresh their device pointer tables when it moves
     std::vector<void*> owned;
     size_t esize() const { return d.dtype == CAR_BF16 ? 2 : 4; }
 };
@@ -77,21 +77,17 @@ struct CarState {
     // decode graph
     cudaGraphExec_t gexec;
     cudaStream_t cap_stream;   // capture happens on a private stream (the legacy default stream cannot capture)
-    bool graph_ok;
+    bool graph_ok; unsigned int graph_pack_gen;
     CarSampling gsp;
     const float* gnoise;
     // persistent decode kernel (decode_persistent.cuh)
     void** pk_ptrs;          // device arrays of per-layer pointers [8][L]
     int* pk_part;            // [4][grid + 1] block offsets per CTA
     uint2 *pk_h2[2], *pk_h1[2], *pk_att[2], *pk_act[2], *pk_qkv[2], *pk_partial[2];
-    int pk_part_slots, pk_grid; bool pk_ok;
-    unsigned int* pk_bar; unsigned int pk_bar_count, pk_tag_base;
+    int pk_part_slots, pk_grid; bool pk_ok; unsigned int pk_ptrs_gen;
+    unsigned int* pk_bar; unsigned int pk_bar_count, pk_tag_gen;
     size_t pk_pkt_bytes; void* pk_pkt_base;
-    // two-chain persistent decode kernel (decode_pk2.cuh): per-micro-batch packet buffers
-    bool p2_ok; int p2_sms; int* p2_part; int p2_part_slots;
-    uint2 *p2_h2[P2_NMB][2], *p2_h1[P2_NMB][2], *p2_att[P2_NMB][2], *p2_act[P2_NMB][2], *p2_qkv[P2_NMB][2], *p2_partial[P2_NMB][2];
-    size_t p2_pkt_bytes; void* p2_pkt_base;
-    unsigned int* p2_bar; unsigned int p2_bar_count, p2_tag_base;
+    long long* pk_step_ts;   // caller-provided device buffer [N] for per-step timestamps (car_state_set_step_timer) or null
     std::vector<void*> owned;
 };
 
@@ -99,6 +95,35 @@ static int alloc_dev(std::vector<void*>& owned, void** p, size_t bytes) {
     CAR_CUDA(cudaMalloc(p, bytes ? bytes : 16));
     owned.push_back(*p);
     return CAR_OK;
+}
+
+// Device buffers that other SMs POLL (packet tags, barrier counters) are initialised with SM stores, not cudaMemset: on B200 a
+// recycled allocation that was zeroed by cudaMemset has been observed to still return the previous owner's packets to strong
+// polling loads (tests/test_ar_gpu.py run as a whole failed deterministically until tags were made unique per state;
+// profiles/r2_stale_tags.md).  Two defences: this fill kernel, and tags that are unique process-wide (pk_alloc_tags).
+__global__ void fill_u32_kernel(unsigned int* __restrict__ p, unsigned int v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+static int fill_u32(void* p, unsigned int v, size_t bytes, cudaStream_t st) {
+    const size_t n = bytes / 4;
+    CAR_LAUNCH(fill_u32_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, st, (unsigned int*)p, v, n);
+    return CAR_OK;
+}
+// Process-wide tag allocator of the persistent decode kernel: every launch gets a fresh, never-reused range of packet tags, so
+// a packet left in memory by ANY earlier launch or state can never be mistaken for a current one.  (2^32 tags last for ~10^5
+// full-size generate() calls; on wrap-around every state re-zeroes its packet buffers before its next launch.)
+static std::atomic<unsigned int> g_pk_tag_next{1u};
+static std::atomic<unsigned int> g_pk_tag_gen{0u};
+static unsigned int pk_alloc_tags(unsigned int span, unsigned int* gen_out) {
+    for (;;) {
+        unsigned int base = g_pk_tag_next.load();
+        if (base > 0xF0000000u || base + span < base) {            // wrap: new generation, tags restart at 1
+            unsigned int expected = base;
+            if (g_pk_tag_next.compare_exchange_strong(expected, 1u)) g_pk_tag_gen.fetch_add(1u);
+            continue;
+        }
+        if (g_pk_tag_next.compare_exchange_weak(base, base + span)) { *gen_out = g_pk_tag_gen.load(); return base; }
+    }
 }
 
 extern "C" const char* car_last_error(void) { return g_car_err.c_str(); }
@@ -109,25 +134,34 @@ extern "C" int64_t car_launch_count(int32_t reset) {
     return v;
 }
 
+// SM count of the CURRENT device (the Python handles make the tensors' device current around every call)
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); cached[dev] = n > 0 ? n : 148; }
+    return cached[dev];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // skinny GEMM dispatch
 // ---------------------------------------------------------------------------------------------------------
 template <int NB, int U, bool NORM>
 static int launch_skinny_bf16_inst(cudaStream_t st, const bf16* A, int lda, const void* Wp, const bf16* nw, float eps,
                                    int M, int nblk, int K, const EpiParams& ep) {
-    static bool attr_set = false;
     const size_t smem = skinny_smem_bytes(K, NB);
-    if (!attr_set) {
+    static DevOnce once;
+    if (once.first()) {
         CAR_CUDA(cudaFuncSetAttribute(skinny_gemm_bf16<NB, U, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CAR_CUDA(cudaFuncSetAttribute(skinny_gemm_bf16<NB, U, NORM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     if (smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "K too large for the shared-memory activation tile");
     dim3 grid((nblk + NB - 1) / NB, (M + 15) / 16);
     if (grid.y == 1) {   // decode shape: never more than one wave of CTAs; a CTA strides over its column groups
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_gemm_bf16<NB, U, NORM>, SK_THREADS, smem);
-        const unsigned cap = 148u * (unsigned)std::max(1, std::min(occ, 2));
+        const unsigned cap = (unsigned)sm_count() * (unsigned)std::max(1, std::min(occ, 2));
         if (grid.x > cap) grid.x = cap;
     }
     const int flags = tune().l2pf ? 1 : 0;
@@ -169,7 +203,7 @@ static int launch_skinny(cudaStream_t st, int dtype, const void* A, int lda, con
     if (mtiles > 1) NB = 4;                       // M-tiled (prefill): maximise reuse of the activation tile
     else {
         // one wave: ceil(nblk / NB) <= 148 where possible (register use makes these 1 CTA / SM kernels)
-        const int want = (nblk + 147) / 148;
+        const int want = (nblk + sm_count() - 1) / sm_count();
         NB = want > 4 ? 8 : (want > 2 ? 4 : (want > 1 ? 2 : 1));
     }
     if (mtiles == 1 && tune().nb[ep.kind] > 0) NB = tune().nb[ep.kind];
@@ -225,6 +259,7 @@ static int model_pack_all(CarModel* m, const CarWeights* w, cudaStream_t st, boo
         CAR_TRY(pack_one(m, st, m->w1[l], m->w3[l], 2 * d.ffn_dim, d.dim, true, &m->g_w13[l], allocate));
         CAR_TRY(pack_one(m, st, m->w2[l], nullptr, d.dim, d.ffn_dim, false, &m->g_w2[l], allocate));
     }
+    ++m->pack_gen;
     CAR_TRY(pack_one(m, st, m->output, nullptr, d.vocab_size, d.dim, false, &m->g_output, allocate));
     if (d.model_type == 1) {
         if (!m->cap_fc1 || !m->cap_fc2) CAR_FAIL(CAR_ERR_ARG, "t2i model needs cap_fc1/cap_fc2");
@@ -296,6 +331,18 @@ static void pk_partition(const CarModelDesc& d, int G, std::vector<int>& table) 
         for (int c = 0; c < G; ++c) table[k * (G + 1) + c + 1] = table[k * (G + 1) + c] + (*cs[k])[c];
 }
 
+// per-layer device pointers of the persistent kernel: packed weights (library-owned), norm weights (borrowed from the module: they
+// move when a parameter tensor is replaced, hence the refresh in launch_pk after car_model_repack), KV caches
+static std::vector<const void*> pk_pointer_table(const CarState* s) {
+    const int L = s->m->d.n_layer;
+    std::vector<const void*> hp(8 * L);
+    for (int l = 0; l < L; ++l) {
+        hp[0 * L + l] = s->m->g_wqkv[l]; hp[1 * L + l] = s->m->g_wo[l]; hp[2 * L + l] = s->m->g_w13[l]; hp[3 * L + l] = s->m->g_w2[l];
+        hp[4 * L + l] = s->m->attention_norm[l]; hp[5 * L + l] = s->m->ffn_norm[l]; hp[6 * L + l] = s->kc[l]; hp[7 * L + l] = s->vc[l];
+    }
+    return hp;
+}
+
 static int pk_state_setup(CarState* s) {
     const CarModelDesc& d = s->m->d;
     int dev = 0, sms = 0;
@@ -305,15 +352,11 @@ static int pk_state_setup(CarState* s) {
     s->pk_grid = G;
     const int nbh = s->b_eff * d.n_head;
     // shapes the kernel is instantiated for (else car_generate falls back to the per-kernel graph chain)
-    s->pk_ok = s->b_eff <= 16 && d.dim % 32 == 0 && d.dim <= 16 * 3 * 32 && d.ffn_dim % 32 == 0 && d.ffn_dim <= 16 * 7 * 32 &&
+    s->pk_ok = s->b_eff <= 16 && d.dim % 32 == 0 && d.dim <= 16 * 3 * 32 && d.dim <= PK_UNIT_KS * 32 /* one ring unit per block of the K = dim GEMMs */ && d.ffn_dim % 32 == 0 && d.ffn_dim <= 16 * 7 * 32 &&
                d.dim / 8 <= 2 * G && d.vocab_size <= 16384 && d.ffn_dim % 8 == 0 && nbh <= 5 * G &&
-               2 * ((d.ffn_dim / 32 + PK_UNIT_KS - 1) / PK_UNIT_KS) <= PK_NSLOT;
+               2 * ((d.ffn_dim / 32 + PK_UNIT_KS - 1) / PK_UNIT_KS) <= PK_NSLOT && L <= PK_MAXL;
     if (!s->pk_ok) return CAR_OK;
-    std::vector<const void*> hp(8 * L);
-    for (int l = 0; l < L; ++l) {
-        hp[0 * L + l] = s->m->g_wqkv[l]; hp[1 * L + l] = s->m->g_wo[l]; hp[2 * L + l] = s->m->g_w13[l]; hp[3 * L + l] = s->m->g_w2[l];
-        hp[4 * L + l] = s->m->attention_norm[l]; hp[5 * L + l] = s->m->ffn_norm[l]; hp[6 * L + l] = s->kc[l]; hp[7 * L + l] = s->vc[l];
-    }
+    std::vector<const void*> hp = pk_pointer_table(s);
     std::vector<int> table;
     pk_partition(d, G, table);
     s->pk_part_slots = G / std::max(1, nbh) + 3;
@@ -332,53 +375,11 @@ static int pk_state_setup(CarState* s) {
         s->pk_act[par] = (uint2*)q; q += a_f; s->pk_qkv[par] = (uint2*)q; q += qkv_b; s->pk_partial[par] = (uint2*)q; q += part_b;
     }
     CAR_CUDA(cudaMemcpy(s->pk_ptrs, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    s->pk_ptrs_gen = s->m->pack_gen;
     CAR_CUDA(cudaMemcpy(s->pk_part, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CAR_CUDA(cudaMemset(s->pk_bar, 0, 64));
-    CAR_CUDA(cudaMemset(s->pk_pkt_base, 0, total));
-    return CAR_OK;
-}
-
-// two-chain kernel: block ownership per CTA rank (same balancing as pk_partition), packet buffers per micro-batch
-static int p2_state_setup(CarState* s) {
-    const CarModelDesc& d = s->m->d;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int G = sms, L = d.n_layer;
-    s->p2_sms = G;
-    std::vector<int> table;
-    pk_partition(d, G, table);
-    int maxq = 0, maxd = 0, maxp = 0, maxh = 0;
-    for (int c = 0; c < G; ++c) {
-        maxq = std::max(maxq, table[0 * (G + 1) + c + 1] - table[0 * (G + 1) + c]);
-        maxd = std::max(maxd, table[1 * (G + 1) + c + 1] - table[1 * (G + 1) + c]);
-        maxp = std::max(maxp, table[2 * (G + 1) + c + 1] - table[2 * (G + 1) + c]);
-        maxh = std::max(maxh, table[3 * (G + 1) + c + 1] - table[3 * (G + 1) + c]);
-    }
-    const int nbh = 8 * d.n_head;                       // pairs of a full micro-batch
-    s->p2_ok = s->b_eff <= 16 && d.dim % 256 == 0 && d.dim <= P2_KPW * P2_WARPS * 32 && d.ffn_dim % 256 == 0 &&
-               d.ffn_dim <= P2_MAXA * P2_WARPS * 32 && d.vocab_size % 4 == 0 && d.vocab_size <= 65536 && maxq <= P2_MAXBLK && maxd <= 2 && 2 * maxp <= P2_MAXBLK &&
-               maxh <= P2_MAXBLK && nbh <= 5 * G;
-    if (!s->p2_ok) return CAR_OK;
-    (void)L;
-    s->p2_part_slots = G / std::max(1, d.n_head) + 3;
-    if (getenv("CAR_TAG_EPOCH")) { static unsigned int epoch = 0; epoch += 0x00100000u; s->p2_tag_base = epoch; }   // dev: unique tags per state   // a pair of the smallest micro-batch (1 row) can span G / H CTAs
-    const size_t a_d = (size_t)(d.dim / 32) * 1024, a_f = (size_t)(d.ffn_dim / 32) * 1024;
-    const size_t qkv_b = (size_t)3 * 8 * d.n_head * 8 * 4 * 8, part_b = (size_t)nbh * s->p2_part_slots * 66 * 8;
-    const size_t per = 2 * (3 * a_d + a_f + qkv_b + part_b);
-    CAR_TRY(alloc_dev(s->owned, (void**)&s->p2_part, table.size() * sizeof(int)));
-    CAR_TRY(alloc_dev(s->owned, (void**)&s->p2_bar, 64));
-    CAR_TRY(alloc_dev(s->owned, &s->p2_pkt_base, P2_NMB * per));
-    s->p2_pkt_bytes = P2_NMB * per;
-    unsigned char* q = (unsigned char*)s->p2_pkt_base;
-    for (int mb = 0; mb < P2_NMB; ++mb)
-        for (int par = 0; par < 2; ++par) {
-            s->p2_h2[mb][par] = (uint2*)q; q += a_d; s->p2_h1[mb][par] = (uint2*)q; q += a_d; s->p2_att[mb][par] = (uint2*)q; q += a_d;
-            s->p2_act[mb][par] = (uint2*)q; q += a_f; s->p2_qkv[mb][par] = (uint2*)q; q += qkv_b; s->p2_partial[mb][par] = (uint2*)q; q += part_b;
-        }
-    CAR_CUDA(cudaMemcpy(s->p2_part, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CAR_CUDA(cudaMemset(s->p2_bar, 0, 64));
-    CAR_CUDA(cudaMemset(s->p2_pkt_base, 0, s->p2_pkt_bytes));
+    CAR_TRY(fill_u32(s->pk_bar, 0u, 64, nullptr));
+    CAR_TRY(fill_u32(s->pk_pkt_base, 0u, total, nullptr));
+    CAR_CUDA(cudaStreamSynchronize(nullptr));          // state creation is rare; the caller's stream may not be ordered after the NULL stream
     return CAR_OK;
 }
 
@@ -398,7 +399,7 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     const size_t es = m->esize();
     const size_t dd = d.dim, F = d.ffn_dim, V = d.vocab_size;
     const size_t MP = (size_t)b_eff * T, MC = (size_t)b_eff * N;
-    s->nsplit = std::max(1, std::min(16, (4 * 148 + b_eff * d.n_head - 1) / (b_eff * d.n_head)));
+    s->nsplit = std::max(1, std::min(16, (4 * sm_count() + b_eff * d.n_head - 1) / (b_eff * d.n_head)));
     if (tune().nsplit > 0) s->nsplit = std::min(32, tune().nsplit);
     int r = CAR_OK;
     auto A = [&](void** p, size_t bytes) { if (r == CAR_OK) r = alloc_dev(s->owned, p, bytes); };
@@ -419,11 +420,10 @@ extern "C" int car_state_create(CarModel* m, int32_t b_eff, int32_t S, int32_t N
     s->done_ctr = s->pos + 1;
     // persistent decode kernel resources (bf16 only)
     s->pk_ptrs = nullptr; s->pk_part = nullptr; s->pk_bar = nullptr; s->pk_grid = 0; s->pk_ok = false;
-    s->pk_bar_count = 0; s->pk_tag_base = 0; s->pk_pkt_base = nullptr; s->pk_pkt_bytes = 0;
-    s->p2_ok = false; s->p2_part = nullptr; s->p2_bar = nullptr; s->p2_bar_count = 0; s->p2_tag_base = 0; s->p2_pkt_base = nullptr; s->p2_pkt_bytes = 0;
+    s->pk_step_ts = nullptr;
+    s->pk_bar_count = 0; s->pk_tag_gen = g_pk_tag_gen.load(); s->pk_pkt_base = nullptr; s->pk_pkt_bytes = 0;
     if (d.dtype == CAR_BF16) {
         int r2 = pk_state_setup(s);
-        if (r2 == CAR_OK) r2 = p2_state_setup(s);
         if (r2 != CAR_OK) { for (void* p : s->owned) cudaFree(p); delete s; return r2; }
     }
     s->emb_mask_store = s->emb_mask;
@@ -439,6 +439,12 @@ extern "C" int car_state_set_emb_mask(CarState* s, const int32_t* emb_mask_dev, 
     CAR_CUDA(cudaMemcpyAsync(s->emb_mask_store, emb_mask_dev, (size_t)s->b_eff * s->T * 4, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
     s->emb_mask = s->emb_mask_store;
+    return CAR_OK;
+}
+
+extern "C" int car_state_set_step_timer(CarState* s, int64_t* step_ns_dev) {
+    if (!s) CAR_FAIL(CAR_ERR_ARG, "null state");
+    s->pk_step_ts = (long long*)step_ns_dev;
     return CAR_OK;
 }
 
@@ -492,19 +498,17 @@ static EpiParams epi_base(int kind) {
 // ---------------------------------------------------------------------------------------------------------
 static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, int M, int N, int K, int act, const void* resid, int ldr,
                         void* out, int ldo) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DevOnce once;
+    if (once.first()) {
         CAR_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-        attr_set = true;
     }
     if (M <= 0 || N <= 0) return CAR_OK;
     static const bool use_tc5 = [] { const char* e = getenv("CAR_TC5"); return e ? atoi(e) != 0 : true; }();
     if (use_tc5 && K % T5_BK == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (resid == nullptr || ldr % 8 == 0)) {
         // tcgen05 path (gemm_tc5.cuh): accumulator in TMEM, operands through shared-memory descriptors
-        static bool attr5 = false;
-        if (!attr5) {
+        static DevOnce once;
+        if (once.first()) {
             CAR_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
-            attr5 = true;
         }
         Tc5P q;
         memset(&q, 0, sizeof(q));
@@ -531,14 +535,14 @@ static int enqueue_block_dense(CarState* s, int l, cudaStream_t st) {
     const int dim = d.dim, F = d.ffn_dim, rows = s->b_eff * s->T;
     CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)s->hP, (const bf16*)m->attention_norm[l], (bf16*)s->t1, dim, d.norm_eps);
     CAR_TRY(dense_linear(st, s->t1, dim, m->wqkv[l], rows, 3 * dim, dim, ACT_NONE, nullptr, 0, s->qkvP, 3 * dim));
-    CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)s->qkvP, s->rope, (bf16*)s->qP, (bf16*)s->kc[l], (bf16*)s->vc[l], rows, s->T, dim,
+    CAR_LAUNCH(rope_kv_write_kernel, sm_count() * 8, 256, 0, st, (const bf16*)s->qkvP, s->rope, (bf16*)s->qP, (bf16*)s->kc[l], (bf16*)s->vc[l], rows, s->T, dim,
                d.n_head, s->S);
     CAR_TRY(launch_attn_prefill<bf16>(s, l, st));
     CAR_TRY(dense_linear(st, s->attnP, dim, m->wo[l], rows, dim, dim, ACT_NONE, s->hP, dim, s->hP, dim));
     CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)s->hP, (const bf16*)m->ffn_norm[l], (bf16*)s->t1, dim, d.norm_eps);
     CAR_TRY(dense_linear(st, s->t1, dim, m->w1[l], rows, F, dim, ACT_NONE, nullptr, 0, s->gP, F));
     CAR_TRY(dense_linear(st, s->t1, dim, m->w3[l], rows, F, dim, ACT_NONE, nullptr, 0, s->uP, F));
-    CAR_LAUNCH(swiglu_kernel, 148 * 8, 256, 0, st, (const bf16*)s->gP, (const bf16*)s->uP, (bf16*)s->actP, (long long)rows * F);
+    CAR_LAUNCH(swiglu_kernel, sm_count() * 8, 256, 0, st, (const bf16*)s->gP, (const bf16*)s->uP, (bf16*)s->actP, (long long)rows * F);
     CAR_TRY(dense_linear(st, s->actP, F, m->w2[l], rows, dim, F, ACT_NONE, s->hP, dim, s->hP, dim));
     return CAR_OK;
 }
@@ -703,11 +707,10 @@ static int fill_sample_args(SampleArgs& a, const CarSampling* sp, int b_eff, int
 }
 
 static int launch_sampler(const SampleArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DevOnce once;
+    if (once.first()) {
         CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     if (a.V > SMP_THREADS * SMP_EPT) CAR_FAIL(CAR_ERR_UNSUPPORTED, "vocab larger than 16384 is not supported by the fused sampler");
     CAR_LAUNCH(sample_kernel, a.B, SMP_THREADS, 0, st, a);
@@ -743,9 +746,17 @@ static int loop_sample_args(CarState* s, const CarSampling* sp, const float* noi
 static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st, const int32_t* forced = nullptr, float* trace = nullptr) {
     const CarModelDesc& d = s->m->d;
     const int L = d.n_layer;
-    if (s->pk_tag_base > 0x7fff0000u) {   // tag wrap: restart the epoch counter on zeroed packets
-        CAR_CUDA(cudaMemsetAsync(s->pk_pkt_base, 0, s->pk_pkt_bytes, st));
-        s->pk_tag_base = 0;
+    if (s->pk_ptrs_gen != s->m->pack_gen) {   // car_model_repack since the table was uploaded: the borrowed norm-weight pointers may have moved
+        const std::vector<const void*> hp = pk_pointer_table(s);
+        CAR_CUDA(cudaMemcpyAsync(s->pk_ptrs, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+        CAR_CUDA(cudaStreamSynchronize(st));                      // hp is a host temporary
+        s->pk_ptrs_gen = s->m->pack_gen;
+    }
+    unsigned int tag_gen = 0;
+    const unsigned int tag_base = pk_alloc_tags((unsigned int)n_tokens * (unsigned int)(L + 1) + 8u, &tag_gen);
+    if (tag_gen != s->pk_tag_gen) {       // the process-wide tag counter wrapped since this state's packets were last zeroed
+        CAR_TRY(fill_u32(s->pk_pkt_base, 0u, s->pk_pkt_bytes, st));
+        s->pk_tag_gen = tag_gen;
     }
     PkParams P;
     memset(&P, 0, sizeof(P));
@@ -763,15 +774,14 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
         P.h2[par] = s->pk_h2[par]; P.h1[par] = s->pk_h1[par]; P.att[par] = s->pk_att[par]; P.act[par] = s->pk_act[par];
         P.qkv[par] = s->pk_qkv[par]; P.partial[par] = s->pk_partial[par];
     }
-    P.part_slots = s->pk_part_slots; P.tag_base = s->pk_tag_base; P.bar = s->pk_bar; P.bar_base = s->pk_bar_count;
+    P.part_slots = s->pk_part_slots; P.tag_base = tag_base; P.bar = s->pk_bar; P.bar_base = s->pk_bar_count;
     P.smp = a; P.n_steps = n_tokens;
-    P.forced = forced; P.forced_ld = n_tokens; P.trace = trace;
+    P.forced = forced; P.forced_ld = n_tokens; P.trace = trace; P.step_ts = s->pk_step_ts;
     if (trace) CAR_CUDA(cudaMemcpyAsync(trace, s->logits, (size_t)s->b_eff * d.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
     { const char* e = getenv("CAR_EXP"); P.exp_flags = e ? atoi(e) : 0; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DevOnce once;
+    if (once.first()) {
         CAR_CUDA(cudaFuncSetAttribute(pk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_TOTAL));
-        attr_set = true;
     }
     int occ = 0;
     CAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk_decode_kernel, PK_THREADS, PK_SMEM_TOTAL));
@@ -786,7 +796,6 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
     void* args[] = {&P};
     CAR_CUDA(cudaLaunchCooperativeKernel((const void*)pk_decode_kernel, dim3(s->pk_grid), dim3(PK_THREADS), args, PK_SMEM_TOTAL, st));
     s->pk_bar_count += (unsigned int)(n_tokens - 1) * (unsigned int)s->pk_grid;        // one grid barrier per decoded token
-    s->pk_tag_base += (unsigned int)(n_tokens - 1) * (unsigned int)(L + 1);
     g_car_launches.fetch_add(1, std::memory_order_relaxed);
     if (tune().dbg) {
         cudaStreamSynchronize(st);
@@ -837,110 +846,6 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
     return CAR_OK;
 }
 
-// the two-chain persistent kernel (decode_pk2.cuh): 2 CTAs of 256 threads per SM, one per micro-batch
-static int launch_pk2(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_t st, const int32_t* forced, float* trace) {
-    const CarModelDesc& d = s->m->d;
-    const int L = d.n_layer;
-    if (s->p2_tag_base > 0x7fff0000u) {
-        CAR_CUDA(cudaMemsetAsync(s->p2_pkt_base, 0, s->p2_pkt_bytes, st));
-        s->p2_tag_base = 0;
-    }
-    P2Params P;
-    memset(&P, 0, sizeof(P));
-    P.dim = d.dim; P.F = d.ffn_dim; P.V = d.vocab_size; P.L = L; P.H = d.n_head; P.T = s->T; P.S = s->S; P.n_img = s->N;
-    P.b_eff = s->b_eff; P.B = a.B; P.eps = d.norm_eps; P.cs = s->cs;
-    // micro-batches: images split in two halves (the first takes the odd one); a single image runs one chain
-    P.nmb = a.B >= 2 ? 2 : 1;
-    P.img_lo[0] = 0; P.img_cnt[0] = (a.B + P.nmb - 1) / P.nmb;
-    P.img_lo[1] = P.img_cnt[0]; P.img_cnt[1] = a.B - P.img_cnt[0];
-    if (P.img_cnt[0] * (a.use_cfg ? 2 : 1) > 8) CAR_FAIL(CAR_ERR_UNSUPPORTED, "more than 8 rows per micro-batch");
-    P.tok_emb = (const bf16*)s->m->tok_emb; P.norm_w = (const bf16*)s->m->norm; P.w_out = (const uint4*)s->m->g_output;
-    void** pp = s->pk_ptrs;
-    P.wqkv = (const uint4* const*)(pp + 0 * L); P.wo = (const uint4* const*)(pp + 1 * L); P.w13 = (const uint4* const*)(pp + 2 * L);
-    P.w2 = (const uint4* const*)(pp + 3 * L); P.attn_norm = (const bf16* const*)(pp + 4 * L); P.ffn_norm = (const bf16* const*)(pp + 5 * L);
-    P.kc = (bf16* const*)(pp + 6 * L); P.vc = (bf16* const*)(pp + 7 * L);
-    for (int j = 0; j < 3; ++j) P.ctrl[j] = (const bf16*)s->ctrl[j];
-    P.has_ctrl = s->has_ctrl ? 1 : 0;
-    P.rope = s->rope; P.emb_mask = s->emb_mask; P.logits = s->logits; P.part = s->p2_part;
-    for (int mb = 0; mb < P2_NMB; ++mb)
-        for (int par = 0; par < 2; ++par) {
-            P.h2[mb][par] = s->p2_h2[mb][par]; P.h1[mb][par] = s->p2_h1[mb][par]; P.att[mb][par] = s->p2_att[mb][par];
-            P.act[mb][par] = s->p2_act[mb][par]; P.qkv[mb][par] = s->p2_qkv[mb][par]; P.partial[mb][par] = s->p2_partial[mb][par];
-        }
-    P.part_slots = s->p2_part_slots; P.tag_base = s->p2_tag_base; P.bar = s->p2_bar; P.bar_base = s->p2_bar_count;
-    P.smp = a; P.n_steps = n_tokens;
-    P.forced = forced; P.forced_ld = n_tokens; P.trace = trace;
-    if (trace) CAR_CUDA(cudaMemcpyAsync(trace, s->logits, (size_t)s->b_eff * d.vocab_size * 4, cudaMemcpyDeviceToDevice, st));
-    { const char* e = getenv("CAR_EXP"); P.exp_flags = e ? atoi(e) : 0; }
-    CAR_CUDA(cudaFuncSetAttribute(pk2_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_TOTAL));
-    int occ = 0;
-    CAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk2_decode_kernel, P2_THREADS, P2_SMEM_TOTAL));
-    if (occ < P.nmb) CAR_FAIL(CAR_ERR_UNSUPPORTED, "two-chain decode kernel: fewer than 2 CTAs fit on an SM");
-    const int grid = P.nmb * s->p2_sms;
-    static long long* mdbg = nullptr;
-    static int* nanflag = nullptr;
-    const size_t nf_n = (size_t)2 * 8 * (L + 1) * 16;
-    const size_t dbg_n = (size_t)grid * 64;
-    if (getenv("CAR_NANCHK")) {
-        if (!nanflag) cudaMalloc(&nanflag, 2 * 8 * 64 * 16 * 4);
-        cudaMemsetAsync(nanflag, 0, nf_n * 4, st);
-        P.nanflag = nanflag;
-    }
-    if (tune().dbg) {
-        if (!mdbg) { cudaMalloc(&mdbg, 2 * 148 * 64 * 8 * 2); }
-        cudaMemsetAsync(mdbg, 0, dbg_n * 8, st);
-        P.dbg = mdbg; P.dbg_step = std::max(0, std::min(n_tokens - 2, tune().dbg));
-    }
-    void* args[] = {&P};
-    CAR_CUDA(cudaLaunchCooperativeKernel((const void*)pk2_decode_kernel, dim3(grid), dim3(P2_THREADS), args, P2_SMEM_TOTAL, st));
-    s->p2_bar_count += (unsigned int)(n_tokens - 1) * (unsigned int)grid;
-    s->p2_tag_base += (unsigned int)(n_tokens - 1) * (unsigned int)(L + 1);
-    g_car_launches.fetch_add(1, std::memory_order_relaxed);
-    if (P.nanflag) {
-        cudaStreamSynchronize(st);
-        std::vector<int> f(nf_n);
-        cudaMemcpy(f.data(), nanflag, nf_n * 4, cudaMemcpyDeviceToHost);
-        int shown = 0;
-        for (int mbi = 0; mbi < 2; ++mbi)
-            for (int sI = 0; sI < 8 && shown < 12; ++sI)
-                for (int l = 0; l <= L && shown < 12; ++l)
-                    for (int k = 0; k < 16; ++k)
-                        if (f[((mbi * 8 + sI) * (L + 1) + l) * 16 + k]) { fprintf(stderr, "[pk2 nan] mb %d step %d layer %d site %d\n", mbi, sI, l, k); ++shown; }
-        if (!shown) fprintf(stderr, "[pk2 nan] none\n");
-    }
-    if (tune().dbg) {
-        cudaStreamSynchronize(st);
-        std::vector<long long> t(dbg_n);
-        cudaMemcpy(t.data(), mdbg, dbg_n * 8, cudaMemcpyDeviceToHost);
-        long long t0 = 0;
-        for (int c = 0; c < grid; ++c) if (t[(size_t)c * 64] && (!t0 || t[(size_t)c * 64] < t0)) t0 = t[(size_t)c * 64];
-        auto stat = [&](int slot, const char* name) {
-            for (int mbi = 0; mbi < P.nmb; ++mbi) {
-                std::vector<long long> v;
-                for (int c = mbi; c < grid; c += P.nmb) if (t[(size_t)c * 64 + slot]) v.push_back(t[(size_t)c * 64 + slot] - t0);
-                if (v.empty()) continue;
-                std::sort(v.begin(), v.end());
-                fprintf(stderr, "[pk2 mb%d] %-22s n=%3zu  min %8.2f  med %8.2f  max %8.2f us\n", mbi, name, v.size(), v.front() * 1e-3, v[v.size() / 2] * 1e-3, v.back() * 1e-3);
-            }
-        };
-        if (!t0) fprintf(stderr, "[pk2] no stamps: rebuild with CAR_PK_TRACE=1 (python -m controlar_b200.build --force)\n");
-        fprintf(stderr, "[pk2] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
-        stat(0, "step start"); stat(1, "sampler done");
-        const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
-        for (int k = 0; k < 5; ++k) {
-            char buf[64];
-            const char* sub[5] = {"start", k == 1 ? "q polled" : "A polled", k == 1 ? "keys done" : "normed", k == 1 ? "end" : "mma done", "end"};
-            for (int j = 0; j < (k == 1 ? 4 : 5); ++j) { snprintf(buf, sizeof buf, "L3 %s %s", nm[k], sub[j]); stat(8 + 8 * k + j, buf); }
-        }
-        stat(3, "head done"); stat(4, "barrier passed");
-    }
-    return CAR_OK;
-}
-static bool use_pk2(const CarState* s) {
-    static const int sel = [] { const char* e = getenv("CAR_PK"); return e ? atoi(e) : 1; }();     // dev: CAR_PK=2 -> experimental two-chain kernel (decode_pk2.cuh; measured slower, see profiles/r2_two_chain_experiment.md)
-    return sel == 2 && s->p2_ok;
-}
-
 extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise, int32_t* tokens_out,
                             void* stream) {
     if (!s || !sp || !tokens_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
@@ -950,8 +855,7 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
     SampleArgs a;
     CAR_TRY(loop_sample_args(s, sp, noise, a));
     if (s->m->d.dtype == CAR_BF16 && tune().mega && s->pk_ok) {
-        if (use_pk2(s)) CAR_TRY(launch_pk2(s, a, n_tokens, st, nullptr, nullptr));
-        else CAR_TRY(launch_pk(s, a, n_tokens, st));
+        CAR_TRY(launch_pk(s, a, n_tokens, st));
         CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, a.B,
                                    cudaMemcpyDeviceToDevice, st));
         CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1 + n_tokens);
@@ -961,7 +865,7 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
     // token 0 from the prefill logits (generate.py:198); its fused tail writes h for position T and bumps pos
     CAR_TRY(launch_sampler(a, st));
     if (n_tokens > 1) {
-        if (!s->graph_ok || !same_sampling(s->gsp, *sp) || s->gnoise != noise) {
+        if (!s->graph_ok || !same_sampling(s->gsp, *sp) || s->gnoise != noise || s->graph_pack_gen != s->m->pack_gen) {
             if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
             cudaGraph_t g = nullptr;
             const long long launched_before = g_car_launches.load();   // captured nodes are not launches yet
@@ -975,7 +879,7 @@ extern "C" int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens
             ce = cudaGraphInstantiate(&s->gexec, g, 0);
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) CAR_FAIL(CAR_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
-            s->graph_ok = true; s->gsp = *sp; s->gnoise = noise;
+            s->graph_ok = true; s->gsp = *sp; s->gnoise = noise; s->graph_pack_gen = s->m->pack_gen;
         }
         const int per_step = s->m->d.n_layer * 5 + 2;
         for (int i = 1; i < n_tokens; ++i) CAR_CUDA(cudaGraphLaunch(s->gexec, st));
@@ -1012,8 +916,7 @@ extern "C" int car_generate_forced(CarState* s, const CarSampling* sp, int32_t n
     cudaStream_t st = (cudaStream_t)stream;
     SampleArgs a;
     CAR_TRY(loop_sample_args(s, sp, noise, a));
-    if (use_pk2(s)) CAR_TRY(launch_pk2(s, a, n_tokens, st, forced_tokens, logits_trace));
-    else CAR_TRY(launch_pk(s, a, n_tokens, st, forced_tokens, logits_trace));
+    CAR_TRY(launch_pk(s, a, n_tokens, st, forced_tokens, logits_trace));
     CAR_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)n_tokens * 4, s->tokens, (size_t)s->N * 4, (size_t)n_tokens * 4, a.B,
                                cudaMemcpyDeviceToDevice, st));
     CAR_LAUNCH(set_int_kernel, 1, 1, 0, st, s->pos, s->T - 1 + n_tokens);

@@ -8,11 +8,8 @@
 #include "vision.cuh"
 
 static int dense(cudaStream_t st, DenseP p, int batch = 1) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CAR_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-        attr_set = true;
-    }
+    static DevOnce once;
+    if (once.first()) CAR_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
     if (p.M <= 0 || p.N <= 0) return CAR_OK;
     if (p.alpha == 0.f) p.alpha = 1.f;
     dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, batch);

@@ -38,6 +38,13 @@ extern std::atomic<long long> g_car_launches;
         if (_r != CAR_OK) return _r; \
     } while (0)
 
+// per-device once-flags (a process-wide `static bool` would configure the first device only; the Python handles make the
+// tensors' device current around every call)
+struct DevOnce {
+    bool done[64] = {false};
+    bool first() { int dev = 0; cudaGetDevice(&dev); if (dev < 0 || dev >= 64) return true; const bool f = !done[dev]; done[dev] = true; return f; }
+};
+
 // every kernel launch goes through this so that car_launch_count() is an honest count
 #define CAR_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                            \

@@ -23,6 +23,7 @@
 #pragma once
 #include "common.cuh"
 #include "sampler.cuh"
+#include "pk_plan.h"
 
 constexpr int PK_WARPS = 16, PK_THREADS = PK_WARPS * 32;
 constexpr int PK_NSLOT = 8;                          // ring slots (power of two)
@@ -35,7 +36,9 @@ constexpr int PK_SMEM_RING = PK_NSLOT * PK_SLOT_BYTES;
 constexpr int PK_SMEM_RED = PK_WARPS * PK_NBMAX * PK_RED * 4;
 constexpr int PK_MAXA = 7;                           // k32-steps per warp (K <= 16 * 7 * 32 = 3584)
 constexpr int PK_MAXA_NORM = 3;                      // ... of the RMS-normalised GEMMs (K = dim <= 1536)
-constexpr int PK_SMEM_MISC = 16 * 16 * 4 + 128 + 128 + 2 * 32 * 8 + 3 * 6 * 128;   // ssq, mbarriers, stream cursor, residual pairs, q/k/v rows
+constexpr int PK_MAXL = 64;                          // layers (shared-memory pointer tables)
+constexpr int PK_SMEM_MISC = 16 * 16 * 4 + 128 + 128 + 2 * 32 * 8 + 3 * 6 * 128     // ssq, mbarriers, stream cursor, residual pairs, q/k/v rows
+                             + 1024 + 4 * PK_MAXL * 8 + PK_WARPS * PK_MAXA_NORM * 32 * 2;   // attention plan, pointer tables, norm weights
 constexpr int PK_SMEM_TOTAL = PK_SMEM_RING + PK_SMEM_RED + PK_SMEM_MISC;
 
 struct PkParams {
@@ -56,6 +59,7 @@ struct PkParams {
     SampleArgs smp;
     int n_steps;                       // tokens to produce (decode iterations = n_steps - 1)
     const int* forced; int forced_ld;  // teacher forcing (parity tests): token fed to the next step = forced[b * forced_ld + step] instead of the sampled one
+    long long* step_ts;                // optional [n_steps]: globaltimer (ns) when CTA 0 enters step s (bench: ms/step vs context length)
     float* trace;                      // optional [n_steps][b_eff][V] fp32: raw model logits of every step (trace[0] = prefill logits, copied by the host)
     int exp_flags;                     // dev experiments (CAR_EXP)
     long long* dbg; int dbg_step;      // dev instrumentation: [grid][64] globaltimer stamps (ns) of one step / layer 3
@@ -135,7 +139,12 @@ struct PkSmem {
     struct PkStream* st;     // weight-stream cursor (touched by the producer thread only)
     uint2* own;              // [2][32] residual-stream pairs of the d-column blocks this CTA owns {rows g, rows g + 8}
     uint32_t* qrow;          // [3][PK_MAXSEG][32] q / newest k / newest v of the attention segments (bf16 pairs)
+    PkAttnPlan* plan;        // this token's attention work split (pk_plan.h)
+    const bf16** kvp;        // [L][2] K / V cache base of every layer (copied from the pointer arrays once per launch)
+    const bf16** nwp;        // [L][2] attention_norm / ffn_norm weights of every layer
+    bf16* nw;                // [<= 1536] the phase's RMSNorm weights, staged by cp.async while the CTA waits for its A packets
 };
+static_assert(sizeof(PkAttnPlan) <= 1024 && PKP_WARPS == PK_WARPS && PKP_MAXSEG == PK_MAXSEG, "plan layout");
 
 // ---------------------------------------------------------------------------------------------------------
 // weight stream: the producer thread walks the CTA's units in consumption order
@@ -330,10 +339,15 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         }
     }
 
+    if (NORM) {   // this phase's RMSNorm weights -> shared memory, asynchronously, while we wait for the A packets
+        const bf16* nwg = kind == 0 ? sm.nwp[2 * l] : kind == 2 ? sm.nwp[2 * l + 1] : P.norm_w;
+        if (tid < (K >> 3))
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pk_smem(sm.nw + tid * 8)), "l"(nwg + tid * 8) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     // ---- A fragments (+ RMSNorm).  Normalised GEMMs have K = dim (<= 3 k-steps per warp, one poll round, norm weights
     // prefetched); the w2 GEMM (K = ffn) polls in two rounds.
     uint32_t alo[PK_MAXA][4], ahi[PK_MAXA][4];
-    uint4 nwv[PK_MAXA_NORM];
     {
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pk_a_buf(P, kind, par));
         const bool need_lo = g < M, need_hi = g + 8 < M;
@@ -360,13 +374,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
     }
     if (stamp) dbg[1] = pk_now();
     PK_W(2);
-    {   // norm weights: requested after the poll (before it they would be spilled across it), used after the CTA barrier;
-        // unconditional definition (a conditionally initialised array would live in local memory)
-        const bf16* nw = kind == 0 ? P.attn_norm[l] : kind == 2 ? P.ffn_norm[l] : P.norm_w;
-#pragma unroll
-        for (int i = 0; i < PK_MAXA_NORM; ++i)
-            nwv[i] = (NORM && i < nst) ? __ldg(reinterpret_cast<const uint4*>(nw + (warp + i * PK_WARPS) * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
-    }
+    if (NORM) asm volatile("cp.async.wait_group 0;" ::: "memory");   // own chunk landed; the CTA barrier below publishes all of them
     if (NORM) {
         float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
@@ -393,12 +401,17 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         __syncthreads();
         if (first) PK_W(4);
         if (NORM && first) {
+            uint4 nwv[PK_MAXA_NORM];
             // row sums of squares: lane i adds row (i & 15) over the 16 warps in order, rsqrt, then rows g / g + 8 by shuffle
             float qs = 0.f;
 #pragma unroll
             for (int w = 0; w < PK_WARPS; ++w) qs += sm.ssq[w * 16 + (lane & 15)];
             const float rs = rsqrtf(qs / (float)K + P.eps);
             const float r_lo = __shfl_sync(0xffffffffu, rs, g), r_hi = __shfl_sync(0xffffffffu, rs, g + 8);
+            // unconditional definition (a conditionally initialised array would live in local memory); k-steps past the end read step 0
+#pragma unroll
+            for (int i = 0; i < PK_MAXA_NORM; ++i)
+                nwv[i] = *reinterpret_cast<const uint4*>(sm.nw + ((i < nst) ? warp + i * PK_WARPS : 0) * 32 + t * 8);
 #pragma unroll
             for (int i = 0; i < PK_MAXA_NORM; ++i) {
                 if (i < nst) {
@@ -423,24 +436,41 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         }
         if (stamp && first) dbg[2] = pk_now();
         if (first) PK_W(5);
-        // ---- MMA: this warp's k-steps against the batch's blocks, B fragments from the ring (32-bit shared addresses;
-        // the unit of (block j, sub-unit) sits in slot (cons + j nsub + sub) mod 8)
+        // ---- MMA: this warp's k-steps against the batch's blocks, B fragments from the ring (32-bit shared addresses).
+        // No per-k-step predicates: a k-step past the end has an all-zero A fragment and re-reads the last real k-step's
+        // weights (finite), so it contributes exactly 0.
         float acc[PK_NBMAX][4];
 #pragma unroll
         for (int j = 0; j < PK_NBMAX; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
         const uint32_t ring_s = pk_smem(sm.ring) + lane * 16;
+        if (kind != 3) {   // K = dim: one unit per block (host-checked: dim <= 40 k32-steps), slot of block j = (cons + j) mod 8
+            uint32_t soff[PK_NBMAX];
 #pragma unroll
-        for (int i = 0; i < PK_MAXA; ++i) {
-            if (i < nst) {
-                const int s = warp + i * PK_WARPS;
+            for (int j = 0; j < PK_NBMAX; ++j) soff[j] = ring_s + ((cons + j) & (PK_NSLOT - 1)) * PK_SLOT_BYTES;
+#pragma unroll
+            for (int i = 0; i < PK_MAXA_NORM; ++i) {
+                const uint32_t koff = (uint32_t)min(warp + i * PK_WARPS, KS - 1) * 512u;
+#pragma unroll
+                for (int j = 0; j < PK_NBMAX; ++j) {
+                    if (j < nb) {
+                        uint4 wf;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wf.x), "=r"(wf.y), "=r"(wf.z), "=r"(wf.w) : "r"(soff[j] + koff));
+                        mma_bf16_16816(acc[j], alo[i][0], ahi[i][0], alo[i][1], ahi[i][1], wf.x, wf.y);
+                        mma_bf16_16816(acc[j], alo[i][2], ahi[i][2], alo[i][3], ahi[i][3], wf.z, wf.w);
+                    }
+                }
+            }
+        } else {           // K = ffn: up to 3 units per block (nb <= PK_NSLOT / nsub blocks per batch: 2 for XL, 4 for small models)
+#pragma unroll
+            for (int i = 0; i < PK_MAXA; ++i) {
+                const int s = min(warp + i * PK_WARPS, KS - 1);
                 const int sub = s / PK_UNIT_KS, so = s - sub * PK_UNIT_KS;
-                const uint32_t u0 = cons + sub;
                 const uint32_t koff = ring_s + so * 512;
 #pragma unroll
                 for (int j = 0; j < PK_NBMAX; ++j) {
                     if (j < nb) {
                         uint4 wf;
-                        const uint32_t addr = koff + ((u0 + j * nsub) & (PK_NSLOT - 1)) * PK_SLOT_BYTES;
+                        const uint32_t addr = koff + ((cons + j * nsub + sub) & (PK_NSLOT - 1)) * PK_SLOT_BYTES;
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wf.x), "=r"(wf.y), "=r"(wf.z), "=r"(wf.w) : "r"(addr));
                         mma_bf16_16816(acc[j], alo[i][0], ahi[i][0], alo[i][1], ahi[i][1], wf.x, wf.y);
                         mma_bf16_16816(acc[j], alo[i][2], ahi[i][2], alo[i][3], ahi[i][3], wf.z, wf.w);
@@ -510,7 +540,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                     if (r_lo < M) pk_st64(ob + ((((size_t)sec * 16 + r_lo) * P.H + head) * 8 + (el >> 3)) * 4 + ((el & 7) >> 1), p_lo, tag);
                     if (r_hi < M) pk_st64(ob + ((((size_t)sec * 16 + r_hi) * P.H + head) * 8 + (el >> 3)) * 4 + ((el & 7) >> 1), p_hi, tag);
                     if (sec > 0) {   // KVCache.update gpt_t2i.py:227-235 (read by later tokens; ordered by the per-token barrier)
-                        bf16* cache = sec == 1 ? P.kc[l] : P.vc[l];
+                        bf16* cache = const_cast<bf16*>(sm.kvp[2 * l + (sec - 1)]);
                         if (r_lo < M) *reinterpret_cast<uint32_t*>(cache + (((size_t)r_lo * P.H + head) * P.S + pos) * 64 + el) = p_lo;
                         if (r_hi < M) *reinterpret_cast<uint32_t*>(cache + (((size_t)r_hi * P.H + head) * P.S + pos) * 64 + el) = p_hi;
                     }
@@ -558,29 +588,14 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// attention phase: the flattened (b, h, key) space is cut into gridDim.x equal ranges
+// attention phase: the flattened (b, h, key) space is cut into gridDim.x equal ranges (work split: pk_plan.h, computed once
+// per token into shared memory — it depends on the context length only, not on the layer)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int pk_cta_of_flat(long long f, long long tot, int G) {
-    int c = (int)((f * G) / tot);
-    while (c + 1 < G && ((long long)(c + 1) * tot) / G <= f) ++c;
-    return c;
-}
-
-struct PkSeg { int bh, b, hd, ks, ke; bool owner; };
-__device__ __forceinline__ PkSeg pk_segment(const PkParams& P, int sg, int nseg, int pair_lo, long long f0, long long f1, int n) {
-    PkSeg r;
-    r.bh = pair_lo + sg; r.b = r.bh / P.H; r.hd = r.bh - r.b * P.H;
-    r.ks = sg == 0 ? (int)(f0 - (long long)r.bh * n) : 0;
-    r.ke = sg == nseg - 1 ? (int)(f1 - (long long)r.bh * n) : n;
-    r.owner = r.ke == n;
-    return r;
-}
-
 // publish one segment's merged (m, l, acc[e]) (thread e = head dimension, 64 threads = two warps): the helper's tagged
 // partial, or the attention output row (combined with the helpers' partials) as A-fragment packets for the wo GEMM
-__device__ __forceinline__ void pk_attn_finalize(const PkParams& P, float Mx, float Ls, float a, const PkSeg& sgm, int e, int n, long long tot,
-                                                 int G, unsigned int tag, int par) {
-    const int first_cta = pk_cta_of_flat((long long)sgm.bh * n, tot, G);
+__device__ __forceinline__ void pk_attn_finalize(const PkParams& P, float Mx, float Ls, float a, const PkSegPlan& sgm, int e, unsigned int tag,
+                                                 int par) {
+    const int first_cta = sgm.first_cta;
     uint2* pb = P.partial[par] + ((size_t)sgm.bh * P.part_slots) * 66;
     if (!sgm.owner) {
         uint2* mine = pb + (size_t)((int)blockIdx.x - first_cta) * 66;
@@ -618,54 +633,32 @@ __device__ __forceinline__ void pk_attn_finalize(const PkParams& P, float Mx, fl
     if ((e & 1) == 0) pk_st64(P.att[par] + pk_a_index(sgm.b, sgm.hd * 64 + e), pk_pack(o, o1), tag);
 }
 
-// Work split: the CTA's flat range [f0, f1) is cut into 16 contiguous warp ranges; a warp range touches at most two
-// (b, h) pairs ("parts").  Within a part the four 8-lane row slots of the warp take rows k0 + sub + 4 i, all loads of up
-// to 8 rows per slot in flight at once; the slots are merged with shuffles and the warp leaves one partial per part in
-// shared memory: entry (warp, part) = {pair, m, l, acc[64]}.
+// Work split: the CTA's flat range is cut into 16 contiguous warp ranges; a warp range touches at most two (b, h) pairs
+// ("parts").  Within a part the four 8-lane row slots of the warp take rows k0 + sub + 4 i, the loads of two blocks of 4 rows
+// per slot in flight at once; the slots are merged with shuffles and the warp leaves one partial per part in shared memory:
+// entry (warp, part) = {-, m, l, -, acc[64]}.
 __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& sm, int layer, int pos, unsigned int tag, int par, long long* dbg) {
-    constexpr int EPL = 8, UNR = 8, ENT = 68;
+    constexpr int EPL = 8, UNR = 4, ENT = 68;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane >> 3, cl = lane & 7;
-    const int n = pos + 1;                                 // keys 0 .. pos; key `pos` is the token being decoded
-    const int nbh = P.b_eff * P.H;
-    const long long tot = (long long)nbh * n;
-    const int G = (int)min((long long)gridDim.x, tot);     // every participating CTA gets at least one key
-    if ((int)blockIdx.x >= G) return;
-    const long long f0 = ((long long)blockIdx.x * tot) / G, f1 = ((long long)(blockIdx.x + 1) * tot) / G;
+    const PkAttnPlan& pl = *sm.plan;
+    if (!pl.active) return;                                // more CTAs than keys (only for tiny contexts)
+    const int n = pos + 1;                                 // keys 0 .. pos; key `pos` is the token being decoded (== pl.n)
+    const int nseg = pl.nseg, pair_lo = pl.pair_lo;
 #ifdef PK_TRACE
     const bool stamp = dbg != nullptr && tid == 0;
 #else
     constexpr bool stamp = false;
 #endif
     if (stamp) dbg[0] = pk_now();
-    const int pair_lo = (int)(f0 / n), pair_hi = (int)((f1 - 1) / n);
-    const int nseg = min(pair_hi - pair_lo + 1, PK_MAXSEG);   // host guarantees <= PK_MAXSEG
     const uint2* qkvb = P.qkv[par];
-    const bf16* kc = P.kc[layer];
-    const bf16* vc = P.vc[layer];
+    const bf16* kc = sm.kvp[2 * layer];
+    const bf16* vc = sm.kvp[2 * layer + 1];
     float* sc = sm.red;                                    // [PK_WARPS][2][ENT]
 
-    // the same key ranges of the NEXT layer (or of layer 0 for the next token) go to L2 now: one bulk prefetch per
-    // contiguous K / V range, capped so that a long context does not flush the weights out of L2
-    if (tid == PK_THREADS - 64 && (P.exp_flags & 8)) {     // (experiment, off: measured 5 % slower at N = 1024)
-        const int ln = layer + 1 < P.L ? layer + 1 : 0;
-        const bf16* kn = P.kc[ln];
-        const bf16* vn = P.vc[ln];
-        int budget = 1536;                                 // rows (128 B each, K and V) per CTA and layer
-        for (int sg = 0; sg < nseg && budget > 0; ++sg) {
-            const PkSeg q = pk_segment(P, sg, nseg, pair_lo, f0, f1, n);
-            const int rows = min(min(q.ke, n - 1) - q.ks, budget);
-            if (rows > 0) {
-                const size_t off = ((size_t)q.bh * P.S + q.ks) * 64;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kn + off), "r"(rows * 128) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vn + off), "r"(rows * 128) : "memory");
-                budget -= rows;
-            }
-        }
-    }
     // q (and, for owner segments, this token's k and v) of every segment -> shared memory, polled in parallel:
     // warp sg, lanes 0-7 q, 8-15 k, 16-23 v (lane & 7 = 16-byte chunk = 4 packets)
     if (warp < nseg && lane < 24) {
-        const PkSeg q = pk_segment(P, warp, nseg, pair_lo, f0, f1, n);
+        const PkSegPlan& q = pl.seg[warp];
         const int sec = lane >> 3;
         if (sec == 0 || q.owner) {
             const uint2* qp = qkvb + (((size_t)(sec * 16 + q.b) * P.H + q.hd) * 8 + (lane & 7)) * 4;
@@ -683,104 +676,106 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     if (stamp) dbg[1] = pk_now();
     __syncthreads();                                       // q/k/v rows visible; the scratch aliases the previous phase's reduction buffer
 
-    {
-        const long long R = f1 - f0;
-        const long long Cw = (R + PK_WARPS - 1) / PK_WARPS;
-        const long long wa = min(f1, f0 + (long long)warp * Cw), wb = min(f1, wa + Cw);
 #pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
-            float* ent = sc + (size_t)(warp * 2 + part) * ENT;
-            // part 0: [wa, min(wb, end of wa's pair)) ; part 1: the rest of the warp range (the next pair)
-            const int bh0 = (int)(wa / n);
-            const long long bound = min(wb, (long long)(bh0 + 1) * n);
-            const long long pa = part == 0 ? wa : bound, pb = part == 0 ? bound : wb;
-            if (pa >= pb) { if (lane == 0) ent[0] = __int_as_float(-1); continue; }     // (warp-uniform)
-            const int bh = (int)(pa / n), b = bh / P.H;
-            const int k0 = (int)(pa - (long long)bh * n), k1 = (int)(pb - (long long)bh * n);
-            const int sg = bh - pair_lo;
-            float qf[EPL];
-            {
-                const uint4 qq = *reinterpret_cast<const uint4*>(sm.qrow + sg * 32 + cl * 4);
-                unpack_bf16x2(qq.x, qf[0], qf[1]); unpack_bf16x2(qq.y, qf[2], qf[3]);
-                unpack_bf16x2(qq.z, qf[4], qf[5]); unpack_bf16x2(qq.w, qf[6], qf[7]);
-            }
-            const bf16* kbase = kc + ((size_t)bh * P.S) * 64 + cl * EPL;
-            const bf16* vbase = vc + ((size_t)bh * P.S) * 64 + cl * EPL;
-            const int* mrow = P.emb_mask ? P.emb_mask + (size_t)b * P.T : nullptr;
-            float m_run = -INFINITY, l_run = 0.f, acc[EPL];
+    for (int part = 0; part < 2; ++part) {
+        float* ent = sc + (size_t)(warp * 2 + part) * ENT;
+        const int4 pt = *reinterpret_cast<const int4*>(&pl.part[warp][part]);   // {bh, b, k0, k1}
+        const int bh = pt.x, b = pt.y, k0 = pt.z, k1 = pt.w;
+        if (k0 >= k1) continue;                            // (warp-uniform)
+        const int sg = bh - pair_lo;
+        float qf[EPL];
+        {
+            const uint4 qq = *reinterpret_cast<const uint4*>(sm.qrow + sg * 32 + cl * 4);
+            unpack_bf16x2(qq.x, qf[0], qf[1]); unpack_bf16x2(qq.y, qf[2], qf[3]);
+            unpack_bf16x2(qq.z, qf[4], qf[5]); unpack_bf16x2(qq.w, qf[6], qf[7]);
+        }
+        const bf16* kbase = kc + ((size_t)bh * P.S) * 64 + cl * EPL;
+        const bf16* vbase = vc + ((size_t)bh * P.S) * 64 + cl * EPL;
+        const int* mrow = P.emb_mask ? P.emb_mask + (size_t)b * P.T : nullptr;
+        float m_run = -INFINITY, l_run = 0.f, acc[EPL];
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-            for (int rb = k0; rb < k1; rb += 4 * UNR) {        // warp-uniform trip count
-                uint4 kraw[UNR], vraw[UNR];
-                int msk[UNR];
+        for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+        // Two blocks of 4 x UNR keys in flight: the loads of block i + 1 are issued before block i is consumed, so the
+        // HBM / L2 latency of the K / V rows overlaps the arithmetic (same 64 raw registers as one 8-row block).
+        // Rows past the end re-read the part's last row (unconditional loads, weight 0).
+        uint4 kA[UNR], vA[UNR], kB[UNR], vB[UNR];
+        int mA[UNR], mB[UNR];
+        auto load_block = [&](uint4 (&kr)[UNR], uint4 (&vr)[UNR], int (&mk)[UNR], const int rb) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int rr = min(rb + sub + 4 * u, k1 - 1);
+                kr[u] = ldg_cg128(kbase + (size_t)rr * 64); vr[u] = ldg_cg128(vbase + (size_t)rr * 64);
+                mk[u] = (mrow != nullptr && rr < P.T) ? __ldg(mrow + rr) : 1;
+            }
+        };
+        // scores of the block's (up to UNR) keys first, ONE running-max update and rescale per block, then the
+        // probability-weighted sum: exp(s - m) and 8 FFMA per key (soft-max is invariant to the reference maximum)
+        auto use_block = [&](uint4 (&kr)[UNR], uint4 (&vr)[UNR], const int (&mk)[UNR], const int rb) {
+            float scu[UNR];
+            float mb = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int r = rb + sub + 4 * u;
+                if (r == n - 1 && r < k1) {   // the newest key / value is this token's: from the QKV packets (owner segments only), not from the cache
+                    kr[u] = *reinterpret_cast<const uint4*>(sm.qrow + (1 * PK_MAXSEG + sg) * 32 + cl * 4);
+                    vr[u] = *reinterpret_cast<const uint4*>(sm.qrow + (2 * PK_MAXSEG + sg) * 32 + cl * 4);
+                }
+                float kf[EPL];
+                unpack_bf16x2(kr[u].x, kf[0], kf[1]); unpack_bf16x2(kr[u].y, kf[2], kf[3]);
+                unpack_bf16x2(kr[u].z, kf[4], kf[5]); unpack_bf16x2(kr[u].w, kf[6], kf[7]);
+                float s = 0.f;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) s = fmaf(qf[e], kf[e], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+                scu[u] = (r < k1 && mk[u] != 0) ? s * 0.125f : -INFINITY;      // 1/sqrt(head_dim = 64); masked / past-the-end -> weight 0
+                mb = fmaxf(mb, scu[u]);
+            }
+            const float m_new = fmaxf(m_run, mb);
+            if (m_new != -INFINITY) {                     // (uniform over the 8 lanes of a row slot)
+                const float corr = __expf(m_run - m_new);   // exp(-inf) = 0 on the first block
+                l_run *= corr;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) acc[e] *= corr;
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
-                    const int r = rb + sub + 4 * u;
-                    const int rr = min(r, k1 - 1);              // slots past the end re-read the last row (unconditional loads)
-                    kraw[u] = ldg_cg128(kbase + (size_t)rr * 64); vraw[u] = ldg_cg128(vbase + (size_t)rr * 64);
-                    msk[u] = (mrow != nullptr && rr < P.T) ? __ldg(mrow + rr) : 1;
-                }
-                // scores of the block's (up to 8) keys first, ONE running-max update and rescale per block, then the
-                // probability-weighted sum: exp(s - m) and 8 FFMA per key (soft-max is invariant to the reference maximum)
-                float sc8[UNR];
-                float mb = -INFINITY;
+                    float vf[EPL];
+                    unpack_bf16x2(vr[u].x, vf[0], vf[1]); unpack_bf16x2(vr[u].y, vf[2], vf[3]);
+                    unpack_bf16x2(vr[u].z, vf[4], vf[5]); unpack_bf16x2(vr[u].w, vf[6], vf[7]);
+                    const float p = __expf(scu[u] - m_new);
+                    l_run += p;
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int r = rb + sub + 4 * u;
-                    if (r == n - 1) {   // the newest key / value is this token's: from the QKV packets, not from the cache
-                        kraw[u] = *reinterpret_cast<const uint4*>(sm.qrow + (1 * PK_MAXSEG + sg) * 32 + cl * 4);
-                        vraw[u] = *reinterpret_cast<const uint4*>(sm.qrow + (2 * PK_MAXSEG + sg) * 32 + cl * 4);
-                    }
-                    float kf[EPL];
-                    unpack_bf16x2(kraw[u].x, kf[0], kf[1]); unpack_bf16x2(kraw[u].y, kf[2], kf[3]);
-                    unpack_bf16x2(kraw[u].z, kf[4], kf[5]); unpack_bf16x2(kraw[u].w, kf[6], kf[7]);
-                    float s = 0.f;
-#pragma unroll
-                    for (int e = 0; e < EPL; ++e) s = fmaf(qf[e], kf[e], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    sc8[u] = (r < k1 && msk[u] != 0) ? s * 0.125f : -INFINITY;      // 1/sqrt(head_dim = 64); masked / past-the-end -> weight 0
-                    mb = fmaxf(mb, sc8[u]);
-                }
-                const float m_new = fmaxf(m_run, mb);
-                if (m_new != -INFINITY) {                     // (uniform over the 8 lanes of a row slot)
-                    const float corr = __expf(m_run - m_new);   // exp(-inf) = 0 on the first block
-                    l_run *= corr;
-#pragma unroll
-                    for (int e = 0; e < EPL; ++e) acc[e] *= corr;
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        float vf[EPL];
-                        unpack_bf16x2(vraw[u].x, vf[0], vf[1]); unpack_bf16x2(vraw[u].y, vf[2], vf[3]);
-                        unpack_bf16x2(vraw[u].z, vf[4], vf[5]); unpack_bf16x2(vraw[u].w, vf[6], vf[7]);
-                        const float p = __expf(sc8[u] - m_new);
-                        l_run += p;
-#pragma unroll
-                        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
-                    }
-                    m_run = m_new;
-                }
-            }
-            // merge the warp's four row slots (lanes 8 apart), fixed order
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-                const float m_o = __shfl_xor_sync(0xffffffffu, m_run, o);
-                const float l_o = __shfl_xor_sync(0xffffffffu, l_run, o);
-                const float m_new = fmaxf(m_run, m_o);
-                const float wA = m_run == -INFINITY ? 0.f : __expf(m_run - m_new);
-                const float wB = m_o == -INFINITY ? 0.f : __expf(m_o - m_new);
-                l_run = l_run * wA + l_o * wB;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) {
-                    const float a_o = __shfl_xor_sync(0xffffffffu, acc[e], o);
-                    acc[e] = acc[e] * wA + a_o * wB;
+                    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
                 }
                 m_run = m_new;
             }
-            if (sub == 0) {
-                if (cl == 0) { ent[0] = __int_as_float(bh); ent[1] = m_run; ent[2] = l_run; }
+        };
+        load_block(kA, vA, mA, k0);
+        for (int rb = k0; rb < k1; rb += 8 * UNR) {        // warp-uniform trip count
+            load_block(kB, vB, mB, rb + 4 * UNR);
+            use_block(kA, vA, mA, rb);
+            load_block(kA, vA, mA, rb + 8 * UNR);
+            if (rb + 4 * UNR < k1) use_block(kB, vB, mB, rb + 4 * UNR);
+        }
+        // merge the warp's four row slots (lanes 8 apart), fixed order
 #pragma unroll
-                for (int e = 0; e < EPL; ++e) ent[4 + cl * EPL + e] = acc[e];
+        for (int o = 8; o <= 16; o <<= 1) {
+            const float m_o = __shfl_xor_sync(0xffffffffu, m_run, o);
+            const float l_o = __shfl_xor_sync(0xffffffffu, l_run, o);
+            const float m_new = fmaxf(m_run, m_o);
+            const float wA = m_run == -INFINITY ? 0.f : __expf(m_run - m_new);
+            const float wB = m_o == -INFINITY ? 0.f : __expf(m_o - m_new);
+            l_run = l_run * wA + l_o * wB;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const float a_o = __shfl_xor_sync(0xffffffffu, acc[e], o);
+                acc[e] = acc[e] * wA + a_o * wB;
             }
+            m_run = m_new;
+        }
+        if (sub == 0) {
+            if (cl == 0) { ent[1] = m_run; ent[2] = l_run; }
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) ent[4 + cl * EPL + e] = acc[e];
         }
     }
     __syncthreads();
@@ -790,26 +785,20 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     {
         const int sg = warp >> 1, e = tid & 63;
         if (sg < nseg) {
-            const PkSeg q = pk_segment(P, sg, nseg, pair_lo, f0, f1, n);
-            const long long R = f1 - f0, Cw = (R + PK_WARPS - 1) / PK_WARPS;
-            const long long ps = max(f0, (long long)q.bh * n), pe = min(f1, (long long)(q.bh + 1) * n);
-            const int w0 = (int)((ps - f0) / Cw), w1 = (int)((pe - 1 - f0) / Cw);
-            const long long pair_start = (long long)q.bh * n;
+            const PkSegPlan& q = pl.seg[sg];
+            const int w0 = q.w0, w1 = q.w1;
+            const unsigned int pm = q.part_mask;
             float Mx = -INFINITY;
-            for (int w = w0; w <= w1; ++w) {
-                const int part = (f0 + (long long)w * Cw >= pair_start) ? 0 : 1;   // the warp range starts inside this pair, or in the one before
-                Mx = fmaxf(Mx, sc[(w * 2 + part) * ENT + 1]);
-            }
+            for (int w = w0; w <= w1; ++w) Mx = fmaxf(Mx, sc[(w * 2 + (int)((pm >> w) & 1u)) * ENT + 1]);
             float Ls = 0.f, a = 0.f;
             for (int w = w0; w <= w1; ++w) {
-                const int part = (f0 + (long long)w * Cw >= pair_start) ? 0 : 1;   // the warp range starts inside this pair, or in the one before
-                const float* en = sc + (w * 2 + part) * ENT;
+                const float* en = sc + (w * 2 + (int)((pm >> w) & 1u)) * ENT;
                 const float mi = en[1];
                 const float wt = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
                 Ls += en[2] * wt;
                 a += en[4 + e] * wt;
             }
-            pk_attn_finalize(P, Mx, Ls, a, q, e, n, tot, G, tag, par);
+            pk_attn_finalize(P, Mx, Ls, a, q, e, tag, par);
         }
     }
     if (stamp) dbg[3] = pk_now();
@@ -848,7 +837,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
         sm.full = reinterpret_cast<uint64_t*>(q); q += 128;
         sm.st = reinterpret_cast<PkStream*>(q); q += 128;
         sm.own = reinterpret_cast<uint2*>(q); q += 2 * 32 * 8;
-        sm.qrow = reinterpret_cast<uint32_t*>(q);
+        sm.qrow = reinterpret_cast<uint32_t*>(q); q += 3 * 6 * 128;
+        sm.plan = reinterpret_cast<PkAttnPlan*>(q); q += 1024;
+        sm.kvp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
+        sm.nwp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
+        sm.nw = reinterpret_cast<bf16*>(q);
     }
     const int tid = threadIdx.x;
     const int G = gridDim.x;
@@ -857,6 +850,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid < P.L) {   // (host-checked: L <= PK_MAXL)
+        sm.kvp[2 * tid] = P.kc[tid]; sm.kvp[2 * tid + 1] = P.vc[tid];
+        sm.nwp[2 * tid] = P.attn_norm[tid]; sm.nwp[2 * tid + 1] = P.ffn_norm[tid];
+    }
     if (tid == PK_THREADS - 32) {
         const int* pt = P.part;
         PkStream& st = *sm.st;
@@ -897,6 +894,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
 #endif
         long long* const dbg_cta = P.dbg + (size_t)blockIdx.x * 64;
         if (dbg_step && tid == 0) dbg_cta[0] = pk_now();
+        if (P.step_ts != nullptr && blockIdx.x == 0 && tid == 0) P.step_ts[step] = pk_now();
         // ---------------- sampler (+ embedding of the sampled token for position pos + 1) ----------------
         if ((int)blockIdx.x < P.B) {
             SampleArgs a = P.smp;
@@ -916,6 +914,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
         if (dbg_step && tid == 0) dbg_cta[1] = pk_now();
         if (step + 1 == P.n_steps) break;
         const int p = pos + 1;                             // position being decoded
+        // attention work split of this token (context length p + 1): 38 threads fill one record each; the previous
+        // token's readers are behind the grid barrier
+        if (tid < 2 * PK_WARPS + PK_MAXSEG) pkp_fill(*sm.plan, tid, (int)blockIdx.x, (int)gridDim.x, P.b_eff * P.H, P.H, p + 1);
+        __syncthreads();
         // layers 0 .. L-1: phases qkv | attention | wo | w1w3 | w2 ; pseudo-layer L: the head.  One call site per
         // phase kind keeps the loop body small enough for the instruction cache.
         for (int l = 0; l <= P.L; ++l) {

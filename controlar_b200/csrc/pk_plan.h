@@ -1,5 +1,4 @@
-// pk_plan.h — per-token work split of the attention phase of the persistent decode kernel (decode_pk2.cuh; 8 warps per CTA,
-// one flat space per micro-batch: b_eff here = rows of the micro-batch, grid = CTAs of the micro-batch).
+// pk_plan.h — per-token work split of the attention phase of the persistent decode kernel (decode_persistent.cuh).
 // Plain integer code, host- and device-compilable: tests/test_pk_plan_cpu.py checks it on the CPU against a brute-force
 // enumeration of the flattened (sequence, head, key) space.
 //
@@ -8,9 +7,9 @@
 //
 //   flat space   f = (b * H + h) * n + key,  tot = b_eff * H * n,  G = min(grid, tot) participating CTAs
 //   CTA c        [f0, f1) = [c tot / G, (c + 1) tot / G)
-//   warp w       [wa, wb) = [min(f1, f0 + w Cw), min(f1, wa + Cw)),  Cw = ceil((f1 - f0) / PKP_WARPS)
+//   warp w       [wa, wb) = [min(f1, f0 + w Cw), min(f1, wa + Cw)),  Cw = ceil((f1 - f0) / 16)
 //   part 0 / 1   the piece of the warp range inside the (b, h) pair of wa / inside the next pair (a warp range touches at
-//                most two pairs when Cw <= n, which holds whenever a CTA range is at most PKP_WARPS pairs long — host-checked)
+//                most two pairs when Cw <= n, which holds whenever a CTA range is at most 16 pairs long — host-checked)
 //   segment s    pair pair_lo + s of the CTA: keys [ks, ke); the CTA owning the pair's LAST key is its owner and combines the
 //                partials of the CTAs before it (first_cta .. c - 1)
 #pragma once
@@ -21,7 +20,7 @@
 #define PK_HD inline
 #endif
 
-constexpr int PKP_WARPS = 8;
+constexpr int PKP_WARPS = 16;
 constexpr int PKP_MAXSEG = 6;
 
 struct PkPart { int bh, b, k0, k1; };                    // keys [k0, k1) of pair bh (sequence b); k0 >= k1: empty

@@ -231,18 +231,56 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
     // ---- draw: arg-max of p (greedy) or of p / q (exponential race); lowest index wins ties
     float best = -1.f; int besti = 0x7fffffff;
     const float* nz = a.noise ? a.noise + ((size_t)(a.noise_per_step ? step : 0) * a.B + b) * V : nullptr;
+    bool raced = false;
+    if (a.sample_logits && nz == nullptr) {
+        // Philox costs ~100 instructions per element and the kept elements (top_k of V) are scattered over all lanes, so the
+        // element-order loop below would run the generator in every (warp, j) iteration for a few lanes each.  Compact the
+        // kept (index, probability) pairs into shared memory first and race over the dense list: the arg-max with the
+        // lowest-index tie-break does not depend on the order, so the token is the same one.
+        constexpr int CAP = 2304;                       // top_k <= 2000 plus ties; larger kept sets take the plain loop
+        __shared__ int s_ci[CAP];
+        __shared__ float s_cp[CAP];
+        __shared__ unsigned s_cn;
+        if (tid == 0) s_cn = 0u;
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int i = tid + j * THREADS;
-        if (i < V && zr[j] > 0.f) {
-            float s = zr[j] / sum;
-            if (a.sample_logits) {
-                float q;
-                if (nz) q = nz[i];
-                else q = exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
-                s = s / q;
+        for (int j = 0; j < EPT; ++j) {
+            const int i = tid + j * THREADS;
+            const bool kept = i < V && zr[j] > 0.f;
+            const unsigned bal = __ballot_sync(0xffffffffu, kept);
+            if (bal != 0u) {                            // (warp-uniform)
+                unsigned base = 0u;
+                if (lane == 0) base = atomicAdd(&s_cn, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned at = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+                if (kept && at < (unsigned)CAP) { s_ci[at] = i; s_cp[at] = zr[j] / sum; }
             }
-            if (s > best || (s == best && i < besti)) { best = s; besti = i; }
+        }
+        __syncthreads();
+        const unsigned nk = s_cn;
+        if (nk <= (unsigned)CAP) {                      // (CTA-uniform)
+            raced = true;
+            for (unsigned c = tid; c < nk; c += THREADS) {
+                const int i = s_ci[c];
+                const float sv = s_cp[c] / exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
+                if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
+            }
+        }
+    }
+    if (!raced) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int i = tid + j * THREADS;
+            if (i < V && zr[j] > 0.f) {
+                float sv = zr[j] / sum;
+                if (a.sample_logits) {
+                    float q;
+                    if (nz) q = nz[i];
+                    else q = exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
+                    sv = sv / q;
+                }
+                if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
+            }
         }
     }
 #pragma unroll

@@ -10,7 +10,23 @@ from typing import List, Optional
 import torch
 
 from . import _lib
+import functools
+
 from ._lib import CarModelDesc, CarSampling, CarWeights, check, cur_stream, dtype_code, _ptr, _ptr_array
+
+
+def _on_own_device(fn):
+    """Run a handle method with the handle's device current: the library launches on the current device and `cur_stream()` is that
+    device's current stream — a model on cuda:1 works without torch.cuda.set_device(1) (the reference wraps its calls
+    in `with torch.device(device)`, generate.py:179-182)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = getattr(self, "device", None)
+        if dev is None or dev.type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class ARModelHandle:
@@ -22,6 +38,9 @@ class ARModelHandle:
         self.handle = C.c_void_p()
         self.version = None
         self._keep = None
+        self._dirty = 0
+        self.device = module.tok_embeddings.weight.device
+        self.generation = 0          # bumped whenever the CarModel handle is re-created: states compare THIS, not the raw pointer
         self._build()
 
     # the tensors whose storage the library borrows
@@ -60,13 +79,27 @@ class ARModelHandle:
         return w, keep
 
     def _signature(self):
+        """Changes when parameters are replaced (data_ptr / dtype / device) or updated through autograd-visible in-place ops
+        (`_version`).  Writes through `p.data` do NOT bump `_version`: call `invalidate()` after such updates."""
         m = self.module
         ps = [m.tok_embeddings.weight, m.output.weight, m.layers[0].attention.wqkv.weight]
         return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in ps) + \
-            (sum(p._version for p in m.parameters()),)
+            (sum(p._version for p in m.parameters()), self._dirty)
 
+    def _layout(self):
+        """What the packed buffers were sized for: a change here needs a new CarModel, anything else a repack in place."""
+        m = self.module
+        w = m.tok_embeddings.weight
+        return (w.dtype, str(w.device), tuple(w.shape), len(m.layers), tuple(m.layers[0].feed_forward.w1.weight.shape))
+
+    def invalidate(self):
+        """Force a repack at the next use (after `param.data` writes, which PyTorch's version counters do not see)."""
+        self._dirty += 1
+
+    @_on_own_device
     def _build(self):
         m = self.module
+        self.device = m.tok_embeddings.weight.device
         cfg = m.config
         dt = m.tok_embeddings.weight.dtype
         d = CarModelDesc(dtype=dtype_code(dt), dim=cfg.dim, n_layer=cfg.n_layer, n_head=cfg.n_head,
@@ -81,13 +114,26 @@ class ARModelHandle:
         check(self.lib.car_model_create(C.byref(d), C.byref(w), cur_stream(), C.byref(self.handle)), "car_model_create")
         self._keep = keep
         self.version = self._signature()
+        self.layout = self._layout()
         self.dtype = dt
         self.desc = d
+        self.generation += 1
 
+    @_on_own_device
     def refresh(self):
-        """Re-create the packed copies if parameters were replaced / updated in place since the last pack."""
-        if self._signature() != self.version:
+        """Bring the packed copies up to date if parameters were replaced / updated since the last pack.  Same layout:
+        `car_model_repack` rewrites the library-owned buffers IN PLACE (the CarModel and every device pointer a live CarState holds
+        stay valid — ADVICE r1: re-creating the model under a live state was a use-after-free).  Different dtype / device / shapes:
+        a new CarModel (generation bumps; `setup_caches` then rebuilds the state)."""
+        if self._signature() == self.version:
+            return
+        if self._layout() != self.layout:
             self._build()
+            return
+        w, keep = self._weights()
+        check(self.lib.car_model_repack(self.handle, C.byref(w), cur_stream()), "car_model_repack")
+        self._keep = keep
+        self.version = self._signature()
 
     def close(self):
         if self.handle:
@@ -108,16 +154,19 @@ class ARStateHandle:
     def __init__(self, model: ARModelHandle, b_eff: int, S: int, N: int, k_caches, v_caches, rope: torch.Tensor):
         self.lib = model.lib
         self.model = model
+        self.device = rope.device
         self.b_eff, self.S, self.N = b_eff, S, N
         self._keep = (list(k_caches), list(v_caches), rope)
         self.handle = C.c_void_p()
         ka, va = _ptr_array(self._keep[0]), _ptr_array(self._keep[1])
-        check(self.lib.car_state_create(model.handle, b_eff, S, N, C.cast(ka, C.POINTER(C.c_void_p)),
-                                        C.cast(va, C.POINTER(C.c_void_p)), _ptr(rope), C.byref(self.handle)),
-              "car_state_create")
+        with torch.cuda.device(self.device):
+            check(self.lib.car_state_create(model.handle, b_eff, S, N, C.cast(ka, C.POINTER(C.c_void_p)),
+                                            C.cast(va, C.POINTER(C.c_void_p)), _ptr(rope), C.byref(self.handle)),
+                  "car_state_create")
         self.V = model.desc.vocab_size
         self.T = model.desc.cls_token_num
 
+    @_on_own_device
     def set_emb_mask(self, emb_mask: Optional[torch.Tensor]):
         if emb_mask is None:
             check(self.lib.car_state_set_emb_mask(self.handle, None, cur_stream()), "car_state_set_emb_mask")
@@ -127,6 +176,7 @@ class ARStateHandle:
         check(self.lib.car_state_set_emb_mask(self.handle, _ptr(em), cur_stream()), "car_state_set_emb_mask")
         self._mask_keep = em
 
+    @_on_own_device
     def prefill(self, cond: torch.Tensor, condition: Optional[torch.Tensor], control_strength: float,
                 all_rows: bool) -> torch.Tensor:
         dev = cond.device
@@ -144,6 +194,7 @@ class ARStateHandle:
         self._io_keep = (cond, condition)
         return out
 
+    @_on_own_device
     def decode_step(self, tok: torch.Tensor, pos: int) -> torch.Tensor:
         tok = tok.reshape(-1).to(torch.int32).contiguous()
         assert tok.numel() == self.b_eff
@@ -152,6 +203,7 @@ class ARStateHandle:
         self._tok_keep = tok
         return out
 
+    @_on_own_device
     def generate(self, sp: CarSampling, n_tokens: int, noise: Optional[torch.Tensor], device) -> torch.Tensor:
         B = self.b_eff // 2 if sp.cfg_scale > 1.0 else self.b_eff
         out = torch.empty((B, n_tokens), dtype=torch.int32, device=device)
@@ -163,6 +215,7 @@ class ARStateHandle:
         self._noise_keep = noise
         return out
 
+    @_on_own_device
     def generate_forced(self, sp: CarSampling, forced: torch.Tensor, trace: bool = True, noise: Optional[torch.Tensor] = None):
         """Teacher-forced device-side loop (car_generate_forced): returns (sampler choices int32 [B, n], logits fp32 [n, b_eff, V])."""
         B = self.b_eff // 2 if sp.cfg_scale > 1.0 else self.b_eff
@@ -178,6 +231,13 @@ class ARStateHandle:
                                            cur_stream()), "car_generate_forced")
         self._noise_keep = (noise, forced)
         return out, tr
+
+    def set_step_timer(self, buf: Optional[torch.Tensor]):
+        """int64 [N] device tensor that receives the GPU globaltimer (ns) at the start of every decode iteration (None = off)."""
+        if buf is not None:
+            assert buf.dtype == torch.int64 and buf.numel() >= self.N and buf.is_cuda
+        check(self.lib.car_state_set_step_timer(self.handle, _ptr(buf)), "car_state_set_step_timer")
+        self._timer_keep = buf
 
     def step_bytes(self, n_context: int) -> int:
         return int(self.lib.car_decode_step_bytes(self.handle, int(n_context)))
@@ -212,8 +272,9 @@ def sample(logits: torch.Tensor, sp: CarSampling, cfg_on: bool = True, step: int
     probs = torch.empty((B, V), dtype=torch.float32, device=logits.device) if return_probs else None
     if noise is not None:
         noise = noise.to(torch.float32).contiguous()
-    check(lib.car_sample(_ptr(logits), b_eff, V, C.byref(sp), 1 if cfg_on else 0, int(step), _ptr(noise), _ptr(idx),
-                         _ptr(probs), cur_stream()), "car_sample")
+    with torch.cuda.device(logits.device):
+        check(lib.car_sample(_ptr(logits), b_eff, V, C.byref(sp), 1 if cfg_on else 0, int(step), _ptr(noise), _ptr(idx),
+                             _ptr(probs), cur_stream()), "car_sample")
     return (idx, probs) if return_probs else idx
 
 

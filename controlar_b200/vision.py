@@ -51,6 +51,27 @@ def _sig(params) -> tuple:
 # ---------------------------------------------------------------------------------------------------------------
 # DINOv2
 # ---------------------------------------------------------------------------------------------------------------
+def _dev_of(module):
+    return next(module.parameters()).device
+
+
+def _on_module_device(attr):
+    """Run a handle method with the device of `getattr(self, attr)`'s parameters current (the library launches on the current device
+    and takes its current stream)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(self, *a, **k):
+            dev = _dev_of(getattr(self, attr))
+            if dev.type != "cuda":
+                return fn(self, *a, **k)
+            with torch.cuda.device(dev):
+                return fn(self, *a, **k)
+        return wrapped
+    return deco
+
+
 class DinoHandle:
     def __init__(self, adapter, adapter_mlp=None):
         self.lib = _lib.lib()
@@ -65,6 +86,7 @@ class DinoHandle:
             ps += list(self.adapter_mlp.parameters())
         return ps
 
+    @_on_module_device("adapter")
     def _build(self):
         m = self.adapter.model
         dt = m.layernorm.weight.dtype
@@ -127,6 +149,7 @@ class DinoHandle:
         self.dtype, self.hidden, self.out_dim = dt, m.hidden, out_dim
         self.sig = _sig(self._params())
 
+    @_on_module_device("adapter")
     def forward(self, x: torch.Tensor, apply_mlp: bool) -> torch.Tensor:
         if _sig(self._params()) != self.sig:
             self._build()
@@ -207,6 +230,7 @@ class VQHandle:
         self.sig = None
         self._build()
 
+    @_on_module_device("vq")
     def _build(self):
         vq = self.vq
         cfg = vq.config
@@ -231,6 +255,7 @@ class VQHandle:
         if _sig(vq_tensor_order(self.vq)) != self.sig:
             self._build()
 
+    @_on_module_device("vq")
     def decode_code(self, codes: torch.Tensor, B: int, h: int, w: int) -> torch.Tensor:
         self._fresh()
         codes = codes.reshape(B, h * w).to(torch.int32).contiguous()
@@ -239,6 +264,7 @@ class VQHandle:
         self._keep = codes
         return out
 
+    @_on_module_device("vq")
     def decode(self, quant: torch.Tensor) -> torch.Tensor:
         self._fresh()
         B, e, h, w = quant.shape
@@ -248,6 +274,7 @@ class VQHandle:
         self._keep = quant
         return out
 
+    @_on_module_device("vq")
     def encode(self, img: torch.Tensor):
         self._fresh()
         B, _, H, W = img.shape

@@ -14,7 +14,12 @@
  *   - every op takes a cudaStream_t (as void*) and is asynchronous on it; the library never calls
  *     cudaDeviceSynchronize and never allocates inside a decode step.
  *   - handles are not thread-safe; distinct handles may be used from distinct threads.
- *   - dtype codes: CAR_BF16 = 0, CAR_F32 = 1 (storage type of weights, activations and KV cache).
+ *   - dtype codes: CAR_BF16 = 0, CAR_F32 = 1 (storage type of weights, activations and KV cache).  There is no CAR_F16:
+ *     the reference's `--precision fp16` (autoregressive/sample/sample_t2i.py:54,197; default bf16) is refused by the Python shells
+ *     with an explicit error.  Reason: the tensor-core operand format (mma.sync / tcgen05 kind::f16 with bf16 inputs), the
+ *     fragment-packed weights and the 8-byte activation packets of the persistent decode kernel are all bf16, and the rounding
+ *     points that parity is defined by (SURVEY.md section 8 a-notes) differ between bf16 and fp16; an fp16 twin of every kernel was
+ *     not built.  fp16 checkpoints can be run by casting the module to bf16 (or fp32) first.
  */
 #ifndef CONTROLAR_B200_H_
 #define CONTROLAR_B200_H_
@@ -131,6 +136,11 @@ int car_sample(const float* logits, int32_t b_eff, int32_t V, const CarSampling*
  * noise: optional fp32 [n_tokens, B, V]. ---- */
 int car_generate(CarState* s, const CarSampling* sp, int32_t n_tokens, const float* noise,
                  int32_t* tokens_out, void* stream);
+
+/* Measurement hook: when step_ns_dev (device, int64 [N]) is non-NULL, every following car_generate on this state records the
+ * GPU globaltimer (ns) at which decode iteration s starts into step_ns_dev[s] (one 8-byte store per token by one thread;
+ * bench.py derives ms/step versus context length from it).  NULL switches it off. */
+int car_state_set_step_timer(CarState* s, int64_t* step_ns_dev);
 
 /* Teacher-forced run of the same device-side loop (parity instrumentation; the reference equivalent is calling
  * Transformer.forward(idx=forced[:, i], input_pos=[T+i]) step by step, gpt_t2i.py:444-470 / generate.py:97-110).

@@ -30,6 +30,28 @@ def _worker(rank: int, world: int, port: int, ret):
         dist.destroy_process_group()
 
 
+def _worker_uneven(rank: int, world: int, port: int, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_bounds(7, world, rank)                      # 7 images on 2 ranks: 4 + 3
+        local = (torch.arange(lo, hi, dtype=torch.int32)[:, None] * 100 + torch.arange(5, dtype=torch.int32)[None, :])
+        ret[rank] = gather_token_grids(local, n_images=7)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_uneven_shards():
+    """n_images % world_size != 0 must neither hang nor mis-size the gather."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_uneven, args=(world, _free_port(), ret), nprocs=world, join=True)
+    want = torch.arange(7, dtype=torch.int32)[:, None] * 100 + torch.arange(5, dtype=torch.int32)[None, :]
+    assert torch.equal(ret[0], want) and torch.equal(ret[1], want)
+
+
 def test_shard_bounds_cover_everything():
     for n in (1, 7, 8, 64):
         for w in (1, 2, 3, 8):

@@ -5,8 +5,7 @@ size-independent properties of the conditional-decoding loop — the oracle need
   * image independence: an image's token grid does not depend on the other images of the batch (rows of the M = 16 GEMMs,
     (b, h) pairs of the attention split and the per-image sampler never mix),
   * every token is a valid code.
-Written after the round-1 GPU budget was spent: first executed by the round-end GPU run (the same shapes and call pattern ran
-many times through scripts/quick_xl.py during development)."""
+NOT YET RUN ON A GPU (written after the round-1 GPU budget was spent; lives on the r2 prep branch until validated)."""
 import pytest
 import torch
 

@@ -74,12 +74,21 @@ def _check(name):
     ref_cols = g["col_logits"].float().permute(1, 0, 2)
     per_step = ((got_cols - ref_cols).double().norm(dim=-1) / ref_cols.double().norm(dim=-1)).amax(dim=1)
     worst_col, worst_col_step = float(per_step.max()), int(g["col_steps"][int(per_step.argmax())])
-    # (3) the sampler's greedy choice given the forced prefix vs the reference's CFG-combined arg-max
+    # (3a) the in-kernel sampler is exact on OUR logits: its greedy choice == arg-max (lowest index on ties) of the CFG-combined trace
+    cs_ = g["cfg_scale"]
+    z = trace[:, B:].float() + (trace[:, :B].float() - trace[:, B:].float()) * cs_        # generate.py:103-107, [n, B, V]
+    zmax = z.max(dim=-1, keepdim=True).values
+    idx = torch.arange(z.shape[-1], device=z.device)
+    own_arg = torch.where(z == zmax, idx, torch.full_like(idx, z.shape[-1])).min(dim=-1).values.t().cpu()     # [B, n]
+    assert torch.equal(own_arg, choice.long()), f"{name}: sampler choice != arg-max of the kernel's own logits at {(own_arg != choice.long()).nonzero()[:4].tolist()}"
+    # (3b) against the reference's greedy choice: every disagreement must be a rounding-level near-tie in the REFERENCE's logits.
+    # near_tie_bound allows each raw logit to land one bf16 ulp off; at 36 layers and contexts > 1000 two-ulp differences occur
+    # (measured logits rel-L2 2.5e-2, profiles/r2_parity.md), hence the factor 2.
     ref_arg = g["argmax_cfg"].long()
     mism = (choice.long() != ref_arg)
     n_mism = int(mism.sum())
     for b, i in mism.nonzero().tolist():
-        bound = near_tie_bound(float(g["raw_absmax"][i]), g["cfg_scale"])
+        bound = 2.0 * near_tie_bound(float(g["raw_absmax"][i]), g["cfg_scale"])
         assert float(g["margin_cfg"][b, i]) <= bound, \
             f"{name}: step {i} image {b}: token differs although the reference's top-2 margin {float(g['margin_cfg'][b, i]):.4f} > near-tie bound {bound:.4f}"
     stats.update(worst_full_rel_l2=worst_full, worst_col_rel_l2=worst_col, worst_col_step=worst_col_step,
