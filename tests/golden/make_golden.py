@@ -206,6 +206,51 @@ def dino_case():
     print("dino ok", flush=True)
 
 
+def vision_512_case():
+    """the vision stages at the REAL size (512 x 512, one image): DINOv2-small features (1025-token attention),
+    VQ decode_code of a 32 x 32 grid (1024-token AttnBlock, the 512^2 level-0 convolutions) and VQ encode indices with the
+    reference's fp32 distances (top-2, to bound near-ties).  Images are stored as fp16 (quantisation 5e-4, far below the
+    tolerance they are compared at)."""
+    from tokenizer.tokenizer_image.vq_model import VQ_models
+    from autoregressive.models.dinov2_adapter import Dinov2_Adapter
+    from oracle.weights import dinov2_shapes, _fill
+    out = {"header": header(), "vq_seed": 3, "dino_seed": 5}
+    # --- DINOv2-small, canny (nearest resize) and depth (bicubic), bf16 like the sampling scripts
+    sd = _fill(dinov2_shapes(384, prefix="model."), 5, 0.02)
+    for ctype in ("canny", "depth"):
+        with fake_hf_cwd("small"), contextlib.redirect_stdout(io.StringIO()):
+            ad = Dinov2_Adapter(adapter_size="small", condition_type=ctype)
+        ad.load_state_dict(sd)
+        ad = ad.eval().to(torch.bfloat16)
+        x = control_map(1, 512, 512, 31, ctype, torch.bfloat16)
+        out[f"dino_small_{ctype}_bf16_512"] = ad(x).clone()
+    # --- VQ-16 decode / encode at 32 x 32 latents
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8)
+    vq.load_state_dict(make_vq_state_dict(seed=3))
+    vq.eval()
+    g = torch.Generator().manual_seed(13)
+    codes = torch.randint(0, 16384, (1, 1024), generator=g)
+    img = vq.decode_code(codes, [1, 8, 32, 32])
+    out["codes"] = codes
+    out["image_absmax"] = img.abs().max().clone()
+    out["image_fp16"] = img.to(torch.float16).clone()
+    x = img.clamp(-1, 1)
+    quant, _, info = vq.encode(x)
+    out["enc_idx"] = info[2].to(torch.int32).clone()
+    z = vq.quant_conv(vq.encoder(x))                                   # [1, 8, 32, 32] pre-quantisation latent
+    out["enc_z"] = z.clone()
+    # the reference's distance matrix (vq_model.py:222-233) and its top-2 per position: margin of the arg-min
+    zf = torch.nn.functional.normalize(z.permute(0, 2, 3, 1).reshape(-1, 8), p=2, dim=-1)
+    e = torch.nn.functional.normalize(vq.quantize.embedding.weight, p=2, dim=-1)
+    d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(e ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, torch.einsum("n d -> d n", e))
+    top2 = torch.topk(-d, 2, dim=1)
+    assert torch.equal(top2.indices[:, 0].to(torch.int32), out["enc_idx"].view(-1))
+    out["enc_second_idx"] = top2.indices[:, 1].to(torch.int32).clone()
+    out["enc_margin"] = (top2.values[:, 0] - top2.values[:, 1]).clone()        # d(second) - d(best) >= 0
+    torch.save(out, os.path.join(OUT, "vision_512.pt"))
+    print("vision_512 ok", tuple(out["image_fp16"].shape), float(out["enc_margin"].min()), flush=True)
+
+
 @contextlib.contextmanager
 def fake_vit_cwd(layers: int = 12):
     """vit_adapter.py:11 loads 'autoregressive/models/vit-small' relative to CWD (ViT-S/16: hidden 384, 6 heads, MLP 1536)."""
@@ -465,6 +510,7 @@ CASES = {
     "vq16": vq_case,
     "dinov2": dino_case,
     "vit": vit_case,
+    "vision_512": vision_512_case,
     "c2i_gptpy_bf16": gptpy_case,
     "train_t2i_small_ac": lambda: train_case("train_t2i_small_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
                                              B=3, H=128, W=128, autocast=torch.bfloat16, use_mask=True, valid=[1, 0, 1]),

@@ -194,3 +194,53 @@ def test_prefill_all_rows_matches_oracle_fp32():
     v0 = model.layers[0].attention.kv_cache.v_cache[:, :, :T].float().cpu()
     assert k0.abs().max() == 0.0                      # zero RoPE rows for the prefix => K == 0 (gpt_t2i.py:518)
     assert rel_l2(v0, orc.v_cache[0][:, :, :T]) < 2e-5
+
+
+def _torch_multinomial_noise(seed, n_steps, B, V):
+    """The Exp(1) draws torch.multinomial(probs, 1) consumes on the reference's CPU run: one `empty_like(probs).exponential_(1)` of
+    shape [B, V] per sampled token, in call order, from the default generator seeded like make_golden.py
+    (ATen multinomial with num_samples == 1: argmax(probs / q); SURVEY.md section 7 hard-part 4)."""
+    torch.manual_seed(seed)
+    return torch.stack([torch.empty(B, V).exponential_(1) for _ in range(n_steps)])
+
+
+def test_sampled_grid_bit_exact_with_torch_noise_fp32():
+    """generate.py:59-74 with sample_logits=True: replaying the reference's own Exp(1) draws through `noise=` reproduces the
+    reference's SAMPLED token grid bit for bit (fp32 checkpoint, top-k 100, CFG 4, masks, control_strength 0.6)."""
+    g, spec, dt, model, sd, cond, masks = _setup("t2i_small_fp32")
+    from controlar_b200.autoregressive.models.generate import generate
+    dev = "cuda"
+    ref = g["sampled_tokens"]
+    B, N = ref.shape
+    noise = _torch_multinomial_noise(g["sampled_seed"], N, B, spec.vocab_size).to(dev)
+    model.adapter.forward = lambda x: x
+    model.adapter_mlp.forward = lambda x: x
+    out = generate(model, cond.to(dev), N, emb_masks=masks.to(dev), cfg_scale=g["cfg_scale"], condition=g["ctrl_in"].to(dev),
+                   control_strength=g["control_strength"], temperature=1.0, top_k=g["sampled_top_k"], top_p=1.0, sample_logits=True,
+                   noise=noise).cpu()
+    assert torch.equal(out, ref), f"first difference at {(out != ref).nonzero()[:3].tolist()}"
+
+
+def test_sampled_choices_with_torch_noise_bf16_persistent_kernel():
+    """The `noise=` path of the persistent decode kernel: teacher-forced along the reference's SAMPLED trajectory (bf16), with the
+    reference's Exp(1) draws, the in-kernel sampler must pick the reference's token at (nearly) every step — a flip needs a
+    bf16-level logit difference to reorder two race candidates."""
+    from controlar_b200 import engine
+    g, spec, dt, model, sd, cond, masks = _setup("t2i_small_bf16")
+    dev = "cuda"
+    ref = g["sampled_tokens"]
+    B, N = ref.shape
+    T = spec.cls_token_num
+    noise = _torch_multinomial_noise(g["sampled_seed"], N, B, spec.vocab_size).to(dev)
+    ctrl_in = g["ctrl_in"].to(dev)
+    c = cond.to(dev)
+    cc = torch.cat([c, torch.zeros_like(c) + model.cls_embedding.uncond_embedding])
+    cond_comb = torch.cat([ctrl_in, torch.zeros_like(ctrl_in)])
+    model.setup_caches(2 * B, T + N, dt, n_img_tokens=N)
+    st = model._car_state
+    st.set_emb_mask(torch.cat([masks, masks]).to(dev))
+    st.prefill(cc, cond_comb, g["control_strength"], all_rows=False)
+    sp = engine.make_sampling(temperature=1.0, top_k=g["sampled_top_k"], top_p=1.0, sample_logits=True, cfg_scale=g["cfg_scale"])
+    choice, _ = st.generate_forced(sp, ref.to(dev), trace=False, noise=noise)
+    agree = float((choice.cpu() == ref).float().mean())
+    assert agree >= 0.9, f"only {agree:.3f} of the sampled choices match the reference"
