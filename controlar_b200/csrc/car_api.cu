@@ -504,18 +504,19 @@ static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, 
     }
     if (M <= 0 || N <= 0) return CAR_OK;
     static const bool use_tc5 = [] { const char* e = getenv("CAR_TC5"); return e ? atoi(e) != 0 : true; }();
-    if (use_tc5 && K % T5_BK == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (resid == nullptr || ldr % 8 == 0)) {
-        // tcgen05 path (gemm_tc5.cuh): accumulator in TMEM, operands through shared-memory descriptors
-        static DevOnce once;
-        if (once.first()) {
-            CAR_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
-        }
+    if (use_tc5 && K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (resid == nullptr || ldr % 8 == 0) &&
+        ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && t5_encoder() != nullptr) {
+        // tcgen05 path (gemm_tc5.cuh): TMA tensor-map loads, accumulator in TMEM, persistent warp-specialised CTAs
+        static DevOnce once5;
+        if (once5.first()) CAR_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+        alignas(64) CUtensorMap mapA, mapB;
+        if (!t5_make_map(&mapA, A, M, K, lda) || !t5_make_map(&mapB, W, N, K, K)) CAR_FAIL(CAR_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         Tc5P q;
         memset(&q, 0, sizeof(q));
-        q.A = (const bf16*)A; q.B = (const bf16*)W; q.M = M; q.N = N; q.K = K; q.lda = lda; q.ldb = K;
+        q.M = M; q.N = N; q.K = K;
         q.resid = (const bf16*)resid; q.ldr = ldr; q.C = (bf16*)out; q.ldc = ldo; q.act = act == ACT_GELU_TANH ? 1 : 0;
-        dim3 grid5((N + T5_BN - 1) / T5_BN, (M + T5_BM - 1) / T5_BM, 1);
-        CAR_LAUNCH(gemm_tc5_kernel, grid5, T5_THREADS, T5_SMEM, st, q);
+        const int ntiles = ((M + T5_BM - 1) / T5_BM) * ((N + T5_BN - 1) / T5_BN);
+        CAR_LAUNCH(gemm_tc5_kernel, std::min(ntiles, sm_count()), T5_THREADS, T5_SMEM, st, mapA, mapB, q);
         return CAR_OK;
     }
     DenseP p;
@@ -817,6 +818,8 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
         if (!t[0] && !t[64]) fprintf(stderr, "[pk] no stamps: rebuild with CAR_PK_TRACE=1 (python -m controlar_b200.build --force)\n");
         fprintf(stderr, "[pk] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
         stat(0, "step start"); stat(1, "sampler done");
+        if (t[40]) fprintf(stderr, "[pk] sampler of CTA 0 (us after its start): loads issued %.2f | row in registers + CFG %.2f | top-k done %.2f | soft-max done %.2f | race done %.2f | CTA done %.2f\n",
+                           0.0, (t[41] - t[40]) * 1e-3, (t[42] - t[40]) * 1e-3, (t[43] - t[40]) * 1e-3, (t[44] - t[40]) * 1e-3, (t[1] - t[40]) * 1e-3);
         const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
         for (int k = 0; k < 5; ++k) {
             char buf[64];
@@ -952,6 +955,14 @@ extern "C" int car_op_linear(int32_t dtype, const void* x, const void* w, const 
     int r = launch_skinny(st, dtype, x, K, packed, nullptr, 0.f, M, N, K, e, false);
     cudaFreeAsync(packed, st);
     return r;
+}
+
+// the dense (M >= 64 rows) tensor-core linear of the prefill / MLP path, exposed for unit tests and micro-benchmarks:
+// y[M,N] = act(x[M,K] · w[N,K]^T) (+ resid), bf16, fp32 accumulate (gemm_tc5.cuh; CAR_TC5=0 selects the mma.sync kernel)
+extern "C" int car_op_dense_linear(const void* x, const void* w, const void* resid, void* y, int32_t M, int32_t N, int32_t K, int32_t act,
+                                   void* stream) {
+    if (!x || !w || !y) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    return dense_linear((cudaStream_t)stream, x, K, w, M, N, K, act ? ACT_GELU_TANH : ACT_NONE, resid, N, y, N);
 }
 
 extern "C" int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void* y, int32_t M, int32_t K, float eps, void* stream) {

@@ -63,7 +63,8 @@ struct SampleArgs {
     int* done_ctr;          // ticket: the last block to finish advances *pos_ptr
     int pos_val;            // position when pos_ptr is null (persistent decode kernel)
     float* ssq_rows;        // optional [16]: sum of squares of the written h rows (index = row), else null
-    int h_reps; long long h_rep_stride;   // extra replicas of h_out (persistent kernel), 0/1 = none
+    int h_reps; long long h_rep_stride;
+    long long* dbg_ts;      // dev (PK_TRACE builds): globaltimer stamps of the sampler's stages, written by thread 0   // extra replicas of h_out (persistent kernel), 0/1 = none
 };
 
 template <typename T>
@@ -128,10 +129,19 @@ template <int THREADS> __device__ __forceinline__ unsigned smp_block_count(unsig
 }
 
 // One CTA per image (b).  The row lives in registers: thread t owns elements t, t+THREADS, ... (EPT of them).
-//   top-k : exact k-th largest by a 32-step bit-wise bisection on the order-preserving integer key (count >= candidate)
+//   top-k : exact k-th largest by a two-level selection (2048-bin histogram over a monotone linear map of the values, then exact
+//           ranks of the few candidates of the boundary bin on the order-preserving integer keys); ties at the threshold are kept
 //   soft-max / nucleus / race only touch the kept elements (k of V), Philox is evaluated per kept element.
+#ifdef PK_TRACE
+#define SMP_STAMP(k) do { if (a.dbg_ts != nullptr && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.dbg_ts[k] = t_; } } while (0)
+#else
+#define SMP_STAMP(k) do { } while (0)
+#endif
+
+constexpr int SMP_SCRATCH = 2304 * 8;     // bytes of shared scratch sample_body needs (selection histogram + candidates, later the compacted race list)
+
 template <int THREADS, int EPT>
-__device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
+__device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, unsigned char* scratch) {
     __shared__ float red_f[THREADS / 32];
     __shared__ unsigned red_u[THREADS / 32];
     __shared__ int red_i[THREADS / 32];
@@ -143,6 +153,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
     bool cfg_on = a.cfg_on != 0;
     if (a.cfg_interval > -1 && step - 1 > a.cfg_interval) cfg_on = false;
 
+    SMP_STAMP(0);
     // ---- CFG combine + temperature (generate.py:103-107, :60)
     float zr[EPT];
     const float* lc = a.logits + (size_t)b * V;
@@ -158,39 +169,110 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
         }
         zr[j] = v;
     }
+    SMP_STAMP(1);
     // ---- top-k threshold (ties at the threshold are kept, generate.py:37).  The row is turned into its order-preserving
     // integer keys in place (the map is a bijection), bisected, and turned back — one register array, not two.
     if (a.top_k > 0 && a.top_k < V) {
+        // Exact radix-style selection in two levels.  Level 1: a 2048-bin histogram over a MONOTONE linear map of the value range
+        // (bin = int((z - lo) * scale): rounding, scaling and truncation are all monotone, so every element of a higher bin is
+        // strictly larger than every element of a lower one; linear bins spread a bell-shaped row over ~all bins, where bins
+        // on the raw float bits would pile it into a handful and serialise the shared-memory atomics).  Level 2: the bin that
+        // contains the k-th largest element holds a few dozen candidates; their exact rank is counted on the order-preserving
+        // integer keys.  Falls back to the bit-wise bisection when that bin is crowded (degenerate rows).
+        constexpr int NBIN = 2048, BPT = NBIN / THREADS, NCAND = 1024;
+        static_assert(NBIN % THREADS == 0, "bins per thread");
+        static_assert((NBIN + NCAND) * 4 <= SMP_SCRATCH, "selection scratch");
+        unsigned* const s_hist = reinterpret_cast<unsigned*>(scratch);
+        unsigned* const s_cand = s_hist + NBIN;
+        __shared__ unsigned s_cnt, s_bin, s_krem, s_thr;
+        float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) zr[j] = __uint_as_float((tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u);
-        // two key bits per step: count the elements >= cand | (1,2,3 << shift) together; one CTA barrier per step
-        // (the per-warp counts go through alternating halves of the scratch array)
-        __shared__ unsigned red_c[2][THREADS / 32][3];
-        unsigned cand = 0;
-#pragma unroll 1
-        for (int shift = 30, it = 0; shift >= 0; shift -= 2, ++it) {
-            const unsigned t1 = cand | (1u << shift), t2 = cand | (2u << shift), t3 = cand | (3u << shift);
-            unsigned c1 = 0, c2 = 0, c3 = 0;
+        for (int j = 0; j < EPT; ++j) if (tid + j * THREADS < V) { lo = fminf(lo, zr[j]); hi = fmaxf(hi, zr[j]); }
+        hi = smp_block_max<THREADS>(hi, red_f);
+        lo = -smp_block_max<THREADS>(-lo, red_f);
+        const float scale = hi > lo ? (float)(NBIN - 1) / (hi - lo) : 0.f;
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const unsigned k = __float_as_uint(zr[j]);
-                c1 += k >= t1 ? 1u : 0u; c2 += k >= t2 ? 1u : 0u; c3 += k >= t3 ? 1u : 0u;
-            }
-            c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
-            if (lane == 0) { red_c[it & 1][warp][0] = c1; red_c[it & 1][warp][1] = c2; red_c[it & 1][warp][2] = c3; }
+        for (int i = 0; i < BPT; ++i) s_hist[tid * BPT + i] = 0u;
+        if (tid == 0) { s_cnt = 0u; s_thr = 0u; }
+        __syncthreads();
+        int mybin[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            mybin[j] = min(max((int)((zr[j] - lo) * scale), 0), NBIN - 1);
+            if (tid + j * THREADS < V) atomicAdd(&s_hist[mybin[j]], 1u);
+        }
+        __syncthreads();
+        {   // bin (from the top) in which the cumulative count reaches k
+            unsigned loc[BPT], mine = 0u;
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) { loc[i] = s_hist[tid * BPT + i]; mine += loc[i]; }
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += v; }
+            if (lane == 0) red_u[warp] = incl;
             __syncthreads();
-            unsigned s1 = 0, s2 = 0, s3 = 0;
+            unsigned above = incl - mine;
+            for (int w = warp + 1; w < THREADS / 32; ++w) above += red_u[w];
+            const unsigned kk = (unsigned)a.top_k;
 #pragma unroll
-            for (int w = 0; w < THREADS / 32; ++w) { s1 += red_c[it & 1][w][0]; s2 += red_c[it & 1][w][1]; s3 += red_c[it & 1][w][2]; }
-            const unsigned kk = (unsigned)a.top_k;                 // counts are non-increasing in the threshold
-            cand = s3 >= kk ? t3 : (s2 >= kk ? t2 : (s1 >= kk ? t1 : cand));
+            for (int i = BPT - 1; i >= 0; --i) {
+                if (above < kk && kk <= above + loc[i]) { s_bin = (unsigned)(tid * BPT + i); s_krem = kk - above; }
+                above += loc[i];
+            }
+        }
+        __syncthreads();
+        const int bsel = (int)s_bin;
+        const unsigned krem = s_krem;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (tid + j * THREADS < V && mybin[j] == bsel) {
+                const unsigned pc = atomicAdd(&s_cnt, 1u);
+                if (pc < (unsigned)NCAND) s_cand[pc] = float_order_key(zr[j]);
+            }
+        }
+        __syncthreads();
+        const unsigned ncand = s_cnt;
+        unsigned cand = 0u;
+        if (ncand <= (unsigned)NCAND) {
+            // exact rank inside the bin: the k_rem-th largest candidate (duplicates counted) is the one with
+            // #{greater} < k_rem <= #{greater or equal}
+            for (unsigned c = tid; c < ncand; c += THREADS) {
+                const unsigned key = s_cand[c];
+                unsigned gt = 0u, ge = 0u;
+                for (unsigned q = 0; q < ncand; ++q) { const unsigned kq = s_cand[q]; gt += kq > key ? 1u : 0u; ge += kq >= key ? 1u : 0u; }
+                if (gt < krem && krem <= ge) s_thr = key;                  // (ties write the same value)
+            }
+            __syncthreads();
+            cand = s_thr;
+        } else {
+            // crowded bin: bit-wise bisection on the integer keys of the whole row, two bits per step
+            __shared__ unsigned red_c[2][THREADS / 32][3];
+#pragma unroll 1
+            for (int shift = 30, it = 0; shift >= 0; shift -= 2, ++it) {
+                const unsigned t1 = cand | (1u << shift), t2 = cand | (2u << shift), t3 = cand | (3u << shift);
+                unsigned c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    const unsigned k = (tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u;
+                    c1 += k >= t1 ? 1u : 0u; c2 += k >= t2 ? 1u : 0u; c3 += k >= t3 ? 1u : 0u;
+                }
+                c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+                if (lane == 0) { red_c[it & 1][warp][0] = c1; red_c[it & 1][warp][1] = c2; red_c[it & 1][warp][2] = c3; }
+                __syncthreads();
+                unsigned s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                for (int w = 0; w < THREADS / 32; ++w) { s1 += red_c[it & 1][w][0]; s2 += red_c[it & 1][w][1]; s3 += red_c[it & 1][w][2]; }
+                const unsigned kk = (unsigned)a.top_k;                 // counts are non-increasing in the threshold
+                cand = s3 >= kk ? t3 : (s2 >= kk ? t2 : (s1 >= kk ? t1 : cand));
+            }
         }
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
-            const unsigned key = __float_as_uint(zr[j]);
-            zr[j] = key < cand ? -INFINITY : __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
+            const unsigned key = (tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u;
+            if (key < cand) zr[j] = -INFINITY;
         }
     }
+    SMP_STAMP(2);
     // ---- soft-max over the kept elements
     float mx = -INFINITY;
 #pragma unroll
@@ -228,6 +310,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) { const int i = tid + j * THREADS; if (i < V) a.probs_out[(size_t)b * V + i] = zr[j] / sum; }
     }
+    SMP_STAMP(3);
     // ---- draw: arg-max of p (greedy) or of p / q (exponential race); lowest index wins ties
     float best = -1.f; int besti = 0x7fffffff;
     const float* nz = a.noise ? a.noise + ((size_t)(a.noise_per_step ? step : 0) * a.B + b) * V : nullptr;
@@ -238,8 +321,9 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
         // kept (index, probability) pairs into shared memory first and race over the dense list: the arg-max with the
         // lowest-index tie-break does not depend on the order, so the token is the same one.
         constexpr int CAP = 2304;                       // top_k <= 2000 plus ties; larger kept sets take the plain loop
-        __shared__ int s_ci[CAP];
-        __shared__ float s_cp[CAP];
+        static_assert(CAP * 8 <= SMP_SCRATCH, "race list scratch");
+        int* const s_ci = reinterpret_cast<int*>(scratch);               // (the selection scratch is dead: block reductions lie in between)
+        float* const s_cp = reinterpret_cast<float*>(scratch + CAP * 4);
         __shared__ unsigned s_cn;
         if (tid == 0) s_cn = 0u;
         __syncthreads();
@@ -303,6 +387,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
     }
     __syncthreads();
 
+    SMP_STAMP(4);
     // ---- fused tail: next step's input rows (cond half b, uncond half b+B)
     if (a.h_out) {
         const int tok = s_tok;
@@ -329,4 +414,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b) {
 }
 
 constexpr int SMP_EPT = 16;                       // V <= SMP_THREADS * SMP_EPT = 16384
-__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) { sample_body<SMP_THREADS, SMP_EPT>(a, blockIdx.x); }
+__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
+    __shared__ __align__(16) unsigned char smp_scratch[SMP_SCRATCH];
+    sample_body<SMP_THREADS, SMP_EPT>(a, blockIdx.x, smp_scratch);
+}

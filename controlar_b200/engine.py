@@ -291,6 +291,18 @@ def op_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     return y.reshape(*x.shape[:-1], N)
 
 
+def op_dense_linear(x: torch.Tensor, w: torch.Tensor, resid: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """y = act(x @ w.T) (+ resid) on the dense tcgen05 path (car_op_dense_linear); bf16."""
+    lib = _lib.lib()
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.car_op_dense_linear(_ptr(x.contiguous()), _ptr(w.detach().contiguous()), _ptr(resid.contiguous()) if resid is not None else None,
+                                      _ptr(y), M, N, K, int(act), cur_stream()), "car_op_dense_linear")
+    return y
+
+
 def op_rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     lib = _lib.lib()
     K = x.shape[-1]

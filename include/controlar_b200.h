@@ -159,6 +159,11 @@ int64_t car_launch_count(int32_t reset);
 /* y[M,N] = act(x[M,K] @ W[N,K]^T (+bias)); act: 0 none, 1 GELU-tanh (gpt_t2i.py:171), 2 GELU-erf. */
 int car_op_linear(int32_t dtype, const void* x, const void* w, const void* bias, void* y, int32_t M, int32_t N,
                   int32_t K, int32_t act, void* stream);
+/* y[M,N] = act(x[M,K] w[N,K]^T) (+ resid[M,N]) on the dense tensor-core path of the prefill (bf16, fp32 accumulate; act 1 = GELU-tanh);
+ * K, N multiples of 8.  Unit-test / micro-benchmark hook for csrc/gemm_tc5.cuh. */
+int car_op_dense_linear(const void* x, const void* w, const void* resid, void* y, int32_t M, int32_t N, int32_t K, int32_t act,
+                        void* stream);
+
 /* RMSNorm.forward (gpt_t2i.py:193-198). */
 int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void* y, int32_t M, int32_t K, float eps,
                    void* stream);

@@ -86,3 +86,24 @@ def test_sampler_philox_is_seeded_and_distributional():
     draws = torch.cat([engine.sample(logits, sp, step=s).cpu() for s in range(200)]).float()
     mean_want = float((p * torch.arange(V)).sum())
     assert abs(float(draws.mean()) - mean_want) < 25.0, (float(draws.mean()), mean_want)
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [(1920, 3584, 1280, 0, False), (1920, 1280, 3584, 0, True), (480, 768, 256, 1, False),
+                                            (1000, 1288, 1096, 0, True), (130, 136, 72, 1, True), (16384, 1280, 1280, 1, False)])
+def test_dense_tcgen05_linear_vs_torch(M, N, K, act, res):
+    """gemm_tc5.cuh (TMA + tcgen05 + TMEM): y = act(x w^T) (+ resid) against an fp32 torch reference of the same rounding points
+    (bf16 product rounding, GELU-tanh in bf16, residual add in bf16); includes M / N / K tails (K % 64 != 0, partial tiles)."""
+    from controlar_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)).to(torch.bfloat16)
+    r = (torch.randn(M, N, device="cuda", generator=g)).to(torch.bfloat16) if res else None
+    y = engine.op_dense_linear(x, w, r, act)
+    ref = (x.float() @ w.float().t()).to(torch.bfloat16).float()
+    if act:
+        ref = torch.nn.functional.gelu(ref, approximate="tanh").to(torch.bfloat16).float()
+    if res:
+        ref = (ref + r.float()).to(torch.bfloat16).float()
+    err = float((y.float() - ref).abs().max())
+    rel = float((y.float() - ref).norm() / ref.norm())
+    assert rel < 4e-3 and err < 0.1, (rel, err)        # one bf16 ulp flips where the fp32 sums differ in the last bit
