@@ -28,6 +28,11 @@ class CarWeights(C.Structure):
                 ("ctl_fc1", C.c_void_p * 3), ("ctl_fc2", C.c_void_p * 3)]
 
 
+class CarTrainWeights(C.Structure):
+    _fields_ = [("w", CarWeights), ("adapter_fc1", C.c_void_p), ("adapter_fc2", C.c_void_p), ("cap_uncond", C.c_void_p),
+                ("adapter_dim", C.c_int32), ("num_classes", C.c_int32)]
+
+
 class CarSampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float),
                 ("sample_logits", C.c_int32), ("cfg_scale", C.c_float), ("cfg_interval", C.c_int32),
@@ -59,6 +64,11 @@ PROTOTYPES = {
                                 C.c_int32, C.c_int32, C.c_void_p]),
     "car_op_dense_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p]),
+    "car_train_create": (C.c_int, [C.POINTER(CarModelDesc), C.POINTER(CarTrainWeights), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_void_p)]),
+    "car_train_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "car_train_destroy": (C.c_int, [C.c_void_p]),
     "car_op_rmsnorm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                  C.c_void_p]),
 }

@@ -263,11 +263,10 @@ class Transformer(nn.Module):
 
     def forward(self, idx, cond_idx, input_pos=None, targets=None, mask=None, valid=None, condition=None,
                 control_strength=1):
-        """Inference branches of reference gpt_t2i.py:409-481 -> (logits fp32, None)."""
+        """Reference gpt_t2i.py:409-484.  Inference branches -> (logits fp32, None); with both ``idx`` and ``cond_idx`` the
+        teacher-forced training branch -> (logits fp32 [B, n+1, V], loss) — forward and loss only, no autograd graph yet."""
         if idx is not None and cond_idx is not None:
-            raise NotImplementedError(
-                "controlar_b200 round 1 covers the inference branches (prefill + KV-cache decode); the teacher-forced "
-                "training branch (reference gpt_t2i.py:420-431) is SURVEY.md §8 row f1 (next)")
+            return self._train_forward(idx, cond_idx, targets, mask, valid, condition)
         if self._car_state is None:
             raise RuntimeError("call setup_caches() before forward(), as generate() does")
         st = self._car_state
@@ -284,6 +283,34 @@ class Transformer(nn.Module):
             self._sync_mask()
         logits = st.decode_step(idx, pos)
         return logits.unsqueeze(1), None
+
+    def _train_forward(self, idx, cond_idx, targets, mask, valid, condition):
+        """Training branch, reference gpt_t2i.py:420-431,451-484 (module in train mode, fp32 parameters, bf16 autocast numerics
+        inside the library).  Like the reference it only works in train mode (in eval mode the reference tuple-unpacks a bare
+        tensor, SURVEY.md §8c gotcha 4)."""
+        if not self.training:
+            raise ValueError("forward(idx, cond_idx) is the training branch: call model.train() first (the reference fails here in eval mode too)")
+        cfg = self.config
+        if max(cfg.token_dropout_p, cfg.resid_dropout_p, cfg.ffn_dropout_p, cfg.attn_dropout_p, cfg.drop_path_rate) > 0:
+            raise NotImplementedError("controlar_b200 training forward: dropout layers with p > 0 are not built yet "
+                                      "(construct the model with token/resid/ffn dropout 0, i.e. --dropout-p 0 --token-dropout-p 0)")
+        B, n = idx.shape
+        th = getattr(self, "_car_train", None)
+        key = tuple(p.data_ptr() for p in self.parameters())
+        if th is None or th.key != key or th.max_batch < B or th.max_img_tokens < n + 1:
+            if th is not None:
+                th.close()
+            th = self._car_train = _engine.ARTrainHandle(self, B, max(n + 1, self.block_size))
+        # CFG drop decision, drawn like the reference (gpt_t2i.py:83,148: torch.rand on the labels' device)
+        forced = getattr(self, "_force_drop_ids", None)
+        if forced is not None:
+            drop = forced.to(device=idx.device).bool()
+        elif cfg.class_dropout_prob > 0:
+            drop = torch.rand(B, device=idx.device) < cfg.class_dropout_prob
+        else:
+            drop = torch.zeros(B, dtype=torch.bool, device=idx.device)
+        feat = self.adapter(condition) if condition is not None else None      # control encoder (CUDA path of vision.py)
+        return th.forward(idx, cond_idx, feat, drop, mask, targets, valid)
 
     def _n_img_check(self, condition):
         if condition.shape[1] != self._n_img:

@@ -13,6 +13,7 @@
 #include "decode_persistent.cuh"
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
+#include "train.cuh"
 #include <algorithm>
 
 thread_local std::string g_car_err;
@@ -970,5 +971,163 @@ extern "C" int car_op_rmsnorm(int32_t dtype, const void* x, const void* w, void*
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CAR_BF16) CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), M, 256, 0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, K, eps);
     else CAR_LAUNCH((rmsnorm_rows_kernel<float>), M, 256, 0, st, (const float*)x, (const float*)w, (float*)y, K, eps);
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// training forward: Transformer.forward(idx, cond_idx, targets, mask, valid, condition) in train mode,
+// fp32 parameters under bf16 autocast — gpt_t2i.py:420-431,451-484.  First correct path: prefill GEMM kernels + train.cuh glue.
+// ---------------------------------------------------------------------------------------------------------
+struct CarTrain {
+    CarModelDesc d;
+    CarTrainWeights w;
+    std::vector<const void*> attention_norm, wqkv, wo, ffn_norm, w1, w3, w2;   // borrowed fp32
+    std::vector<bf16*> b_wqkv, b_wo, b_w1, b_w3, b_w2;                          // owned bf16 casts, refreshed every forward
+    bf16 *b_out, *b_cap1, *b_cap2, *b_cond1, *b_cond2, *b_ctl1[3], *b_ctl2[3], *b_ad1, *b_ad2;
+    int maxB, maxN, maxS;
+    const float* rope;
+    float *h, *nll;
+    bf16 *x, *qkv, *q, *kc, *vc, *att, *g, *u, *act, *o, *cin, *ctmp, *ctok, *cadd, *lg;
+    std::vector<void*> owned;
+};
+
+static int tr_cast(cudaStream_t st, const void* src, bf16* dst, long long n) {
+    CAR_LAUNCH(tr_cast_bf16_kernel, (int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st, (const float*)src, dst, n);
+    return CAR_OK;
+}
+static int tr_grid(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
+// MLP.forward gpt_t2i.py:177-181 on bf16 operands: out = fc2(gelu_tanh(fc1 x))
+static int tr_mlp(cudaStream_t st, const bf16* x, int rows, int K, const bf16* fc1, const bf16* fc2, int d, bf16* tmp, bf16* out) {
+    CAR_TRY(dense_linear(st, x, K, fc1, rows, d, K, ACT_GELU_TANH, nullptr, 0, tmp, d));
+    return dense_linear(st, tmp, d, fc2, rows, d, d, ACT_NONE, nullptr, 0, out, d);
+}
+
+extern "C" int car_train_create(const CarModelDesc* desc, const CarTrainWeights* w, int32_t max_batch, int32_t max_img_tokens,
+                                const float* rope_table, void* stream, CarTrain** out) {
+    if (!desc || !w || !out || !rope_table) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    const CarModelDesc& d = *desc;
+    if (d.dtype != CAR_F32) CAR_FAIL(CAR_ERR_UNSUPPORTED, "training forward takes the fp32 master weights (bf16 autocast is applied inside)");
+    if (d.dim % 64 != 0 || d.dim / d.n_head != 64 || d.n_layer % 3 != 0 || d.ffn_dim % 8 != 0 || d.vocab_size % 8 != 0 || w->adapter_dim % 8 != 0 ||
+        (d.model_type == 1 && d.caption_dim % 8 != 0))
+        CAR_FAIL(CAR_ERR_UNSUPPORTED, "shape not supported (head_dim 64, dims multiple of 8, n_layer multiple of 3)");
+    if (max_batch <= 0 || max_img_tokens <= 0) CAR_FAIL(CAR_ERR_ARG, "bad capacity");
+    (void)stream;
+    CarTrain* t = new CarTrain();
+    t->d = d; t->w = *w; t->rope = rope_table;
+    t->maxB = max_batch; t->maxN = max_img_tokens; t->maxS = d.cls_token_num + max_img_tokens - 1;
+    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, V = d.vocab_size;
+    auto copyp = [&](std::vector<const void*>& v, const void* const* src) { v.assign(src, src + L); };
+    copyp(t->attention_norm, w->w.attention_norm); copyp(t->wqkv, w->w.wqkv); copyp(t->wo, w->w.wo); copyp(t->ffn_norm, w->w.ffn_norm);
+    copyp(t->w1, w->w.w1); copyp(t->w3, w->w.w3); copyp(t->w2, w->w.w2);
+    int rc = CAR_OK;
+    auto A = [&](bf16** p, size_t elems) { if (rc == CAR_OK) rc = alloc_dev(t->owned, (void**)p, elems * 2); };
+    t->b_wqkv.resize(L); t->b_wo.resize(L); t->b_w1.resize(L); t->b_w3.resize(L); t->b_w2.resize(L);
+    for (int l = 0; l < L; ++l) {
+        A(&t->b_wqkv[l], (size_t)3 * dim * dim); A(&t->b_wo[l], (size_t)dim * dim);
+        A(&t->b_w1[l], (size_t)F * dim); A(&t->b_w3[l], (size_t)F * dim); A(&t->b_w2[l], (size_t)dim * F);
+    }
+    A(&t->b_out, (size_t)V * dim);
+    t->b_cap1 = t->b_cap2 = nullptr;
+    if (d.model_type == 1) { A(&t->b_cap1, (size_t)dim * d.caption_dim); A(&t->b_cap2, (size_t)dim * dim); }
+    A(&t->b_cond1, (size_t)dim * dim); A(&t->b_cond2, (size_t)dim * dim);
+    for (int j = 0; j < 3; ++j) { A(&t->b_ctl1[j], (size_t)dim * dim); A(&t->b_ctl2[j], (size_t)dim * dim); }
+    A(&t->b_ad1, (size_t)dim * w->adapter_dim); A(&t->b_ad2, (size_t)dim * dim);
+    const size_t R = (size_t)t->maxB * t->maxS, RC = (size_t)t->maxB * t->maxN;
+    if (rc == CAR_OK) rc = alloc_dev(t->owned, (void**)&t->h, R * dim * 4);
+    if (rc == CAR_OK) rc = alloc_dev(t->owned, (void**)&t->nll, RC * 4);
+    A(&t->x, std::max(R * dim, (size_t)t->maxB * d.cls_token_num * std::max(d.caption_dim, dim)));
+    A(&t->qkv, R * 3 * dim); A(&t->q, R * dim); A(&t->kc, R * dim); A(&t->vc, R * dim); A(&t->att, R * dim);
+    A(&t->g, R * F); A(&t->u, R * F); A(&t->act, R * F); A(&t->o, R * dim);
+    A(&t->cin, RC * dim); A(&t->ctmp, std::max(RC, (size_t)t->maxB * d.cls_token_num) * dim); A(&t->ctok, RC * dim); A(&t->cadd, RC * dim);
+    A(&t->lg, RC * V);
+    if (rc != CAR_OK) { for (void* p : t->owned) cudaFree(p); delete t; return rc; }
+    *out = t;
+    return CAR_OK;
+}
+
+extern "C" int car_train_destroy(CarTrain* t) {
+    if (!t) return CAR_OK;
+    for (void* p : t->owned) cudaFree(p);
+    delete t;
+    return CAR_OK;
+}
+
+extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const int32_t* idx, const void* cond, const void* feat,
+                                 const uint8_t* drop_ids, const uint8_t* mask, const int32_t* targets, const float* valid,
+                                 float* logits_out, float* loss_out, void* stream) {
+    if (!t || !idx || !cond || !drop_ids) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (B <= 0 || B > t->maxB || n_img < 2 || n_img > t->maxN) CAR_FAIL(CAR_ERR_ARG, "batch / token count beyond the capacity given to car_train_create");
+    if ((loss_out != nullptr) != (targets != nullptr)) CAR_FAIL(CAR_ERR_ARG, "loss_out and targets go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CarModelDesc& d = t->d;
+    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, V = d.vocab_size, T = d.cls_token_num, H = d.n_head;
+    const int n = n_img - 1, S = T + n, R = B * S, RC = B * n_img;
+    if (S > T + d.block_size) CAR_FAIL(CAR_ERR_ARG, "sequence longer than the RoPE table");
+    // 0. autocast: bf16 copies of every nn.Linear weight, re-cast each forward (the fp32 masters may have been stepped)
+    for (int l = 0; l < L; ++l) {
+        CAR_TRY(tr_cast(st, t->wqkv[l], t->b_wqkv[l], (long long)3 * dim * dim)); CAR_TRY(tr_cast(st, t->wo[l], t->b_wo[l], (long long)dim * dim));
+        CAR_TRY(tr_cast(st, t->w1[l], t->b_w1[l], (long long)F * dim)); CAR_TRY(tr_cast(st, t->w3[l], t->b_w3[l], (long long)F * dim));
+        CAR_TRY(tr_cast(st, t->w2[l], t->b_w2[l], (long long)dim * F));
+    }
+    CAR_TRY(tr_cast(st, t->w.w.output, t->b_out, (long long)V * dim));
+    if (d.model_type == 1) { CAR_TRY(tr_cast(st, t->w.w.cap_fc1, t->b_cap1, (long long)dim * d.caption_dim)); CAR_TRY(tr_cast(st, t->w.w.cap_fc2, t->b_cap2, (long long)dim * dim)); }
+    if (feat) {
+        CAR_TRY(tr_cast(st, t->w.w.cond_fc1, t->b_cond1, (long long)dim * dim)); CAR_TRY(tr_cast(st, t->w.w.cond_fc2, t->b_cond2, (long long)dim * dim));
+        for (int j = 0; j < 3; ++j) { CAR_TRY(tr_cast(st, t->w.w.ctl_fc1[j], t->b_ctl1[j], (long long)dim * dim)); CAR_TRY(tr_cast(st, t->w.w.ctl_fc2[j], t->b_ctl2[j], (long long)dim * dim)); }
+        CAR_TRY(tr_cast(st, t->w.adapter_fc1, t->b_ad1, (long long)dim * t->w.adapter_dim)); CAR_TRY(tr_cast(st, t->w.adapter_fc2, t->b_ad2, (long long)dim * dim));
+    }
+    // 1. prefix rows: CaptionEmbedder (token_drop, cap_proj) gpt_t2i.py:145-162 or LabelEmbedder :78-97; image-token rows :423
+    if (d.model_type == 1) {
+        CAR_LAUNCH(tr_caption_select_kernel, tr_grid((long long)B * T * d.caption_dim), 256, 0, st, (const float*)cond, (const float*)t->w.cap_uncond,
+                   drop_ids, t->x, B, T, d.caption_dim);
+        CAR_TRY(tr_mlp(st, t->x, B * T, d.caption_dim, t->b_cap1, t->b_cap2, dim, t->ctmp, t->o));
+        CAR_LAUNCH(tr_put_rows_bf16_kernel, tr_grid((long long)B * T * dim), 256, 0, st, (const bf16*)t->o, t->h, B, T, S, 0, dim);
+    } else {
+        CAR_LAUNCH(tr_embed_rows_kernel, B, 256, 0, st, (const float*)t->w.w.label_table, (const int*)cond, 1, drop_ids, t->w.num_classes, t->h, B, 1, S, 0, dim);
+    }
+    CAR_LAUNCH(tr_embed_rows_kernel, B * n, 256, 0, st, (const float*)t->w.w.tok_embeddings, (const int*)idx, n, (const unsigned char*)nullptr, 0, t->h, B, n, S, T, dim);
+    // 2. control tokens: adapter_mlp -> token_drop -> condition_mlp  gpt_t2i.py:424-427 (feat = the control encoder's output tokens)
+    if (feat) {
+        CAR_TRY(tr_mlp(st, (const bf16*)feat, RC, t->w.adapter_dim, t->b_ad1, t->b_ad2, dim, t->ctmp, t->cin));
+        CAR_LAUNCH(tr_zero_dropped_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->cin, drop_ids, B, (long long)n_img * dim);
+        CAR_TRY(tr_mlp(st, t->cin, RC, dim, t->b_cond1, t->b_cond2, dim, t->ctmp, t->ctok));
+    }
+    // 3. blocks  gpt_t2i.py:456-468, TransformerBlock :303-307
+    const int step3 = L / 3;
+    static bool attr_set = false;
+    const size_t att_smem = (size_t)TRA_WARPS * S * 4;
+    if (att_smem > 48 * 1024 && !attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(tr_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (att_smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "sequence too long for the plain attention kernel");
+    for (int l = 0; l < L; ++l) {
+        if (feat && l % step3 == 0) {
+            CAR_TRY(tr_mlp(st, t->ctok, RC, dim, t->b_ctl1[l / step3], t->b_ctl2[l / step3], dim, t->ctmp, t->cadd));
+            CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->h, (const bf16*)t->cadd, B, n_img, S, T - 1, dim);
+        }
+        CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->attention_norm[l], t->x, dim, d.norm_eps, S, S, 0);
+        CAR_TRY(dense_linear(st, t->x, dim, t->b_wqkv[l], R, 3 * dim, dim, ACT_NONE, nullptr, 0, t->qkv, 3 * dim));
+        CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)t->qkv, t->rope, t->q, t->kc, t->vc, R, S, dim, H, S);
+        CAR_LAUNCH(tr_attention_kernel, (unsigned)(((long long)B * H * S + TRA_WARPS - 1) / TRA_WARPS), TRA_WARPS * 32, att_smem, st, (const bf16*)t->q,
+                   (const bf16*)t->kc, (const bf16*)t->vc, mask, B, H, S, t->att);
+        CAR_TRY(dense_linear(st, t->att, dim, t->b_wo[l], R, dim, dim, ACT_NONE, nullptr, 0, t->o, dim));
+        CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
+        CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->ffn_norm[l], t->x, dim, d.norm_eps, S, S, 0);
+        CAR_TRY(dense_linear(st, t->x, dim, t->b_w1[l], R, F, dim, ACT_NONE, nullptr, 0, t->g, F));
+        CAR_TRY(dense_linear(st, t->x, dim, t->b_w3[l], R, F, dim, ACT_NONE, nullptr, 0, t->u, F));
+        CAR_LAUNCH(swiglu_kernel, 148 * 8, 256, 0, st, (const bf16*)t->g, (const bf16*)t->u, t->act, (long long)R * F);
+        CAR_TRY(dense_linear(st, t->act, F, t->b_w2[l], R, dim, F, ACT_NONE, nullptr, 0, t->o, dim));
+        CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
+    }
+    // 4. head on rows T-1 .. S-1 of every sample (gpt_t2i.py:469-473), loss :474-481
+    CAR_LAUNCH(tr_rmsnorm_kernel, RC, 256, 0, st, (const float*)t->h, (const float*)t->w.w.norm, t->x, dim, d.norm_eps, n_img, S, T - 1);
+    CAR_TRY(dense_linear(st, t->x, dim, t->b_out, RC, V, dim, ACT_NONE, nullptr, 0, t->lg, V));
+    if (targets) {
+        CAR_LAUNCH(tr_ce_rows_kernel, RC, 256, 0, st, (const bf16*)t->lg, (const int*)targets, logits_out, t->nll, V);
+        CAR_LAUNCH(tr_ce_reduce_kernel, 1, 1024, 0, st, (const float*)t->nll, valid, B, n_img, loss_out);
+    } else if (logits_out) {
+        CAR_LAUNCH(tr_put_rows_bf16_kernel, tr_grid((long long)RC * V), 256, 0, st, (const bf16*)t->lg, logits_out, 1, RC, RC, 0, V);
+    }
     return CAR_OK;
 }

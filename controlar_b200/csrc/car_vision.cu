@@ -557,3 +557,17 @@ extern "C" int car_vq_encode(CarVQ* m, const float* img, int32_t B, int32_t H, i
     if (quant_out) CAR_LAUNCH(nhwc_to_nchw_f32_kernel, gsz((long long)npix * d.embed_dim), 256, 0, st, zq, quant_out, B, h * w, d.embed_dim);
     return CAR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// antialiased bilinear resize (row f2): width pass into tmp, height pass into out
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int car_resize_bilinear_aa(const float* in, int32_t B, int32_t Cc, int32_t H, int32_t W, float* out, int32_t OH, int32_t OW,
+                                      float* tmp, void* stream) {
+    if (!in || !out || !tmp) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (B <= 0 || Cc <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) CAR_FAIL(CAR_ERR_ARG, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n1 = (long long)B * Cc * H * OW, n2 = (long long)B * Cc * OH * OW;
+    CAR_LAUNCH(resize_aa_axis_kernel, (int)std::min<long long>((n1 + 255) / 256, 148 * 16), 256, 0, st, in, tmp, (long long)B * Cc * H, W, OW, 1);
+    CAR_LAUNCH(resize_aa_axis_kernel, (int)std::min<long long>((n2 + 255) / 256, 148 * 16), 256, 0, st, (const float*)tmp, out, (long long)B * Cc, H, OH, OW);
+    return CAR_OK;
+}

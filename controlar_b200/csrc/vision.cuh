@@ -273,3 +273,38 @@ __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __re
         y[i] = x[((size_t)b * HW + pix) * d + k];
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Antialiased bilinear resize along ONE axis: F.interpolate(x, size, mode='bilinear', align_corners=False,
+// antialias=True) of the multi-resolution training scripts (autoregressive/train/train_t2i_depth_multiscale.py:44-56) is two of
+// these passes, width then height.  Third-party arithmetic (ATen _upsample_bilinear2d_aa, HelperInterpBase::
+// _compute_indices_min_size_weights_aa; restated in oracle/resize_oracle.py): triangle filter stretched by the down-scale factor,
+// every weight computed in fp32 exactly as ATen does — scale = in / out, support = max(scale, 1), centre = scale (i + 0.5),
+// taps [max(int(c - support + 0.5), 0), min(int(c + support + 0.5), in)), w_j = max(0, 1 - |(j - c + 0.5) / max(scale, 1)|) / sum.
+// Tensor viewed as [outer][n_in][inner] -> [outer][n_out][inner] (inner = 1: width pass; inner = W_out: height pass).
+// HBM-bound gather: consecutive threads take consecutive `inner` (height pass) or consecutive outputs of a row (width pass).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void resize_aa_axis_kernel(const float* __restrict__ in, float* __restrict__ out, long long outer, int n_in, int n_out, int inner) {
+    const float scale = (float)n_in / (float)n_out;
+    const float support = scale >= 1.f ? scale : 1.f;
+    const float inv = scale >= 1.f ? 1.f / scale : 1.f;
+    const long long total = outer * n_out * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % inner);
+        const long long t = i / inner;
+        const int o = (int)(t % n_out);
+        const long long r = t / n_out;
+        const float c = scale * ((float)o + 0.5f);
+        const int lo = max((int)(c - support + 0.5f), 0);
+        const int hi = min((int)(c + support + 0.5f), n_in);
+        float tot = 0.f;
+        for (int j = lo; j < hi; ++j) tot += fmaxf(0.f, 1.f - fabsf(((float)j - c + 0.5f) * inv));
+        const float* src = in + (r * n_in) * inner + q;
+        float acc = 0.f;
+        for (int j = lo; j < hi; ++j) {
+            const float w = fmaxf(0.f, 1.f - fabsf(((float)j - c + 0.5f) * inv)) / tot;
+            acc += w * src[(size_t)j * inner];
+        }
+        out[i] = acc;
+    }
+}

@@ -147,6 +147,86 @@ class ARModelHandle:
             pass
 
 
+class ARTrainHandle:
+    """CarTrain: the teacher-forced training forward (reference gpt_t2i.py:420-431,451-484) on the module's fp32 parameters
+    under bf16-autocast numerics.  Weights are borrowed (re-cast to bf16 inside every forward, like autocast does)."""
+
+    def __init__(self, module, max_batch: int, max_img_tokens: int):
+        from ._lib import CarTrainWeights
+        self.lib = _lib.lib()
+        m = module
+        cfg = m.config
+        if m.tok_embeddings.weight.dtype != torch.float32:
+            raise NotImplementedError("controlar_b200 training forward: fp32 parameters (bf16 autocast is applied inside), as the train scripts keep them")
+        w, keep = ARModelHandle._weights(self_like(m))
+        tw = CarTrainWeights()
+        tw.w = w
+        tw.adapter_fc1 = _ptr(m.adapter_mlp.fc1.weight.detach()); tw.adapter_fc2 = _ptr(m.adapter_mlp.fc2.weight.detach())
+        tw.adapter_dim = m.adapter_mlp.fc1.weight.shape[1]
+        tw.num_classes = cfg.num_classes
+        if m.model_type == "t2i":
+            unc = m.cls_embedding.uncond_embedding.detach().to(torch.float32).contiguous()
+            keep.append(unc)
+            tw.cap_uncond = _ptr(unc)
+        d = CarModelDesc(dtype=_lib.CAR_F32, dim=cfg.dim, n_layer=cfg.n_layer, n_head=cfg.n_head,
+                         ffn_dim=m.layers[0].feed_forward.w1.weight.shape[0], vocab_size=cfg.vocab_size,
+                         cls_token_num=cfg.cls_token_num, block_size=cfg.block_size,
+                         caption_dim=cfg.caption_dim if m.model_type == "t2i" else 0,
+                         model_type=1 if m.model_type == "t2i" else 0, norm_eps=cfg.norm_eps, rope_base=cfg.rope_base)
+        dev = m.tok_embeddings.weight.device
+        self.rope = m.freqs_cis.to(device=dev, dtype=torch.float32).contiguous()
+        self.handle = C.c_void_p()
+        check(self.lib.car_train_create(C.byref(d), C.byref(tw), max_batch, max_img_tokens, _ptr(self.rope), cur_stream(), C.byref(self.handle)),
+              "car_train_create")
+        self._keep = (keep, tw)
+        self.max_batch, self.max_img_tokens = max_batch, max_img_tokens
+        self.V, self.T = cfg.vocab_size, cfg.cls_token_num
+        self.key = tuple(p.data_ptr() for p in m.parameters())
+
+    def forward(self, idx, cond, feat, drop_ids, mask, targets, valid):
+        B, n = idx.shape
+        n_img = n + 1
+        dev = idx.device
+        idx = idx.to(torch.int32).contiguous()
+        cond = cond.to(torch.int32).contiguous() if cond.dtype in (torch.int64, torch.int32) else cond.to(torch.float32).contiguous()
+        feat = None if feat is None else feat.to(torch.bfloat16).contiguous()
+        drop = drop_ids.to(torch.uint8).contiguous()
+        S = self.T + n
+        m8 = None
+        if mask is not None:
+            m8 = mask.reshape(B, S, S).to(torch.uint8).contiguous()
+        tg = None if targets is None else targets.to(torch.int32).contiguous()
+        vf = None if valid is None else valid.to(torch.float32).contiguous()
+        logits = torch.empty(B, n_img, self.V, device=dev, dtype=torch.float32)
+        loss = torch.empty(1, device=dev, dtype=torch.float32) if tg is not None else None
+        check(self.lib.car_train_forward(self.handle, B, n_img, _ptr(idx), _ptr(cond), None if feat is None else _ptr(feat), _ptr(drop),
+                                         None if m8 is None else _ptr(m8), None if tg is None else _ptr(tg),
+                                         None if vf is None else _ptr(vf), _ptr(logits), None if loss is None else _ptr(loss), cur_stream()),
+              "car_train_forward")
+        return logits, (None if loss is None else loss[0])
+
+    def close(self):
+        if self.handle:
+            self.lib.car_train_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _ModuleView:
+    def __init__(self, module):
+        self.module = module
+
+
+def self_like(module):
+    """ARModelHandle._weights only reads ``self.module``."""
+    return _ModuleView(module)
+
+
 class ARStateHandle:
     """CarState: KV caches (PyTorch-owned, reference layout), control tokens, scratch, the persistent decode kernel's packet
     buffers (and the CUDA graph of the per-kernel fallback chain)."""

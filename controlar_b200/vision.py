@@ -38,6 +38,8 @@ _PROTOS = {
     "car_vq_create": (C.c_int, [C.POINTER(CarVQDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "car_vq_decode_code": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "car_vq_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "car_resize_bilinear_aa": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p]),
     "car_vq_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "car_vq_destroy": (C.c_int, [C.c_void_p]),
 }
@@ -292,3 +294,15 @@ class VQHandle:
                 self.lib.car_vq_destroy(self.handle)
         except Exception:
             pass
+
+
+def resize_bilinear_aa(x: torch.Tensor, size) -> torch.Tensor:
+    """`F.interpolate(x.float(), size=size, mode='bilinear', align_corners=False, antialias=True)` — the multi-resolution training
+    scripts' `random_sample_scale` (reference autoregressive/train/train_t2i_depth_multiscale.py:44-56) — on the GPU library."""
+    x = x.to(torch.float32).contiguous()
+    B, Cc, H, W = x.shape
+    OH, OW = int(size[0]), int(size[1])
+    out = torch.empty(B, Cc, OH, OW, device=x.device, dtype=torch.float32)
+    tmp = torch.empty(B, Cc, H, OW, device=x.device, dtype=torch.float32)
+    check(_lib.lib().car_resize_bilinear_aa(_ptr(x), B, Cc, H, W, _ptr(out), OH, OW, _ptr(tmp), cur_stream()), "car_resize_bilinear_aa")
+    return out

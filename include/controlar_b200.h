@@ -215,6 +215,43 @@ int car_vq_encode(CarVQ* m, const float* img_nchw, int32_t B, int32_t H, int32_t
                   void* stream);
 int car_vq_destroy(CarVQ* m);
 
+/* =====================================================================================================
+ * Training forward: Transformer.forward(idx, cond_idx, targets, mask, valid, condition) with the module
+ * in train mode (autoregressive/models/gpt_t2i.py:420-431,451-484) as the train scripts run it — fp32 parameters under bf16
+ * autocast (autoregressive/train/train_t2i_canny.py:166-167, train_c2i_canny.py:200-201).  Dropout layers at p = 0; the CFG
+ * drop decision (gpt_t2i.py:83,116,148: torch.rand(B) < class_dropout_prob) is drawn by the caller and passed in.
+ * Forward + loss only (no gradients yet).
+ * ===================================================================================================== */
+typedef struct CarTrain CarTrain;
+typedef struct CarTrainWeights {
+    CarWeights  w;             /* the transformer's fp32 master tensors (same keys as above; desc.dtype = CAR_F32) */
+    const void* adapter_fc1;   /* adapter_mlp.fc1.weight [d, adapter_dim] fp32 */
+    const void* adapter_fc2;   /* adapter_mlp.fc2.weight [d, d]           fp32 */
+    const void* cap_uncond;    /* cls_embedding.uncond_embedding [T, caption_dim] fp32 (t2i), else NULL */
+    int32_t     adapter_dim;   /* 384 (DINOv2-small / ViT-S) | 768 (DINOv2-base) */
+    int32_t     num_classes;   /* c2i: row of the dropped label in cls_embedding.embedding_table */
+} CarTrainWeights;
+/* Workspaces are sized for max_batch sequences of cls_token_num + max_img_tokens - 1 rows.  Weights and rope_table
+ * (fp32 [T + block_size, 32, 2], as for car_state_create) are borrowed until car_train_destroy. */
+int car_train_create(const CarModelDesc* desc, const CarTrainWeights* weights, int32_t max_batch, int32_t max_img_tokens,
+                     const float* rope_table, void* stream, CarTrain** out);
+/* idx int32 [B, n_img - 1] (the scripts pass z[:, :-1]); cond: t2i fp32 [B, T, caption_dim] | c2i int32 [B];
+ * feat: control-encoder output tokens bf16 [B, n_img, adapter_dim] (= self.adapter(condition)) or NULL;
+ * drop_ids uint8 [B]; mask uint8 [B, S, S] with S = T + n_img - 1 (1 = attend) or NULL = causal (is_causal=True);
+ * targets int32 [B, n_img] (with loss_out, else both NULL); valid fp32 [B] or NULL (plain mean);
+ * logits_out fp32 [B, n_img, V] or NULL; loss_out fp32 [1]. */
+int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const int32_t* idx, const void* cond, const void* feat,
+                      const uint8_t* drop_ids, const uint8_t* mask, const int32_t* targets, const float* valid,
+                      float* logits_out, float* loss_out, void* stream);
+int car_train_destroy(CarTrain* t);
+
+/* ---- antialiased bilinear resize in front of the online VQ encode of the multi-resolution training scripts:
+ * F.interpolate(x.float(), size=(OH, OW), mode='bilinear', align_corners=False, antialias=True),
+ * autoregressive/train/train_t2i_depth_multiscale.py:44-56.  in fp32 [B, C, H, W] -> out fp32 [B, C, OH, OW];
+ * tmp: caller-provided fp32 scratch [B, C, H, OW]. ---- */
+int car_resize_bilinear_aa(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, float* out, int32_t OH, int32_t OW,
+                           float* tmp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
