@@ -819,8 +819,10 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
         if (!t[0] && !t[64]) fprintf(stderr, "[pk] no stamps: rebuild with CAR_PK_TRACE=1 (python -m controlar_b200.build --force)\n");
         fprintf(stderr, "[pk] step %d, times relative to the first CTA entering the sampler; layer 3 phases\n", P.dbg_step);
         stat(0, "step start"); stat(1, "sampler done");
-        if (t[40]) fprintf(stderr, "[pk] sampler of CTA 0 (us after its start): loads issued %.2f | row in registers + CFG %.2f | top-k done %.2f | soft-max done %.2f | race done %.2f | CTA done %.2f\n",
-                           0.0, (t[41] - t[40]) * 1e-3, (t[42] - t[40]) * 1e-3, (t[43] - t[40]) * 1e-3, (t[44] - t[40]) * 1e-3, (t[1] - t[40]) * 1e-3);
+        if (t[48]) fprintf(stderr, "[pk] sampler top-k of CTA 0: histogram built %.2f | boundary bin found %.2f | candidates gathered %.2f\n",
+                           (t[53] - t[48]) * 1e-3, (t[54] - t[48]) * 1e-3, (t[55] - t[48]) * 1e-3);
+        if (t[48]) fprintf(stderr, "[pk] sampler of CTA 0 (us after its start): loads issued %.2f | row in registers + CFG %.2f | top-k done %.2f | soft-max done %.2f | race done %.2f | CTA done %.2f\n",
+                           0.0, (t[49] - t[48]) * 1e-3, (t[50] - t[48]) * 1e-3, (t[51] - t[48]) * 1e-3, (t[52] - t[48]) * 1e-3, (t[1] - t[48]) * 1e-3);
         const char* nm[5] = {"qkv", "attn", "wo", "w13", "w2"};
         for (int k = 0; k < 5; ++k) {
             char buf[64];

@@ -202,6 +202,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
             if (tid + j * THREADS < V) atomicAdd(&s_hist[mybin[j]], 1u);
         }
         __syncthreads();
+        SMP_STAMP(5);
         {   // bin (from the top) in which the cumulative count reaches k
             unsigned loc[BPT], mine = 0u;
 #pragma unroll
@@ -221,6 +222,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
             }
         }
         __syncthreads();
+        SMP_STAMP(6);
         const int bsel = (int)s_bin;
         const unsigned krem = s_krem;
 #pragma unroll
@@ -231,6 +233,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
             }
         }
         __syncthreads();
+        SMP_STAMP(7);
         const unsigned ncand = s_cnt;
         unsigned cand = 0u;
         if (ncand <= (unsigned)NCAND) {

@@ -18,7 +18,17 @@ def test_resize_bilinear_aa(shape):
     got = resize_bilinear_aa(x.cuda(), (oh, ow)).cpu()
     assert got.shape == (2, 3, oh, ow)
     ref_t = F.interpolate(x.cuda(), size=(oh, ow), mode="bilinear", align_corners=False, antialias=True).cpu()
-    assert float((got - ref_t).abs().max()) < 1e-3
+    ref_c = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)      # ATen's CPU kernel (the oracle's pin)
+    e_cuda, e_cpu, cuda_vs_cpu = (float((got - ref_t).abs().max()), float((got - ref_c).abs().max()), float((ref_t - ref_c).abs().max()))
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "resize.jsonl"), "a") as fh:
+        fh.write(json.dumps({"shape": shape, "max_abs_vs_torch_cuda": e_cuda, "max_abs_vs_torch_cpu": e_cpu, "torch_cuda_vs_torch_cpu": cuda_vs_cpu}) + "\n")
+    # bar: 1e-3 of the 0..255 range against ATen's CPU kernel (separable two-pass, what oracle/resize_oracle.py restates); ATen's CUDA
+    # kernel is a one-pass 2-D gather with its own summation order — the product must be as close to it as ATen's two kernels are
+    # to each other (+ 1e-3)
+    assert e_cpu < 1e-3, (e_cpu, e_cuda, cuda_vs_cpu)
+    assert e_cuda < cuda_vs_cpu + 1e-3, (e_cpu, e_cuda, cuda_vs_cpu)
     if h * w <= 96 * 96:
         assert float((got - bilinear_aa_resize(x, (oh, ow))).abs().max()) < 1e-3
 
