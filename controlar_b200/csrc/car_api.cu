@@ -829,6 +829,10 @@ static int launch_pk(CarState* s, const SampleArgs& a, int n_tokens, cudaStream_
             const char* sub[5] = {"start", k == 1 ? "q polled" : "A polled", k == 1 ? "keys done" : "weights+norm", k == 1 ? "end" : "mma done", "end"};
             for (int j = 0; j < (k == 1 ? 4 : 5); ++j) { snprintf(buf, sizeof buf, "L3 %s %s", nm[k], sub[j]); stat(8 + 8 * k + j, buf); }
         }
+        {
+            const char* sub[5] = {"head start", "head A polled", "head weights+norm", "head mma done (batch 0)", "head end (batch 0)"};
+            for (int j = 0; j < 5; ++j) stat(56 + j, sub[j]);
+        }
         stat(3, "head done"); stat(4, "barrier passed");
         {   // per-warp stamps of one CTA (77): min / max over the 16 warps, relative to the phase's first stamp
             const char* wn[11] = {"start", "prepoll", "A loaded", "ssq out", "sync1", "normed", "mma", "red out", "sync2", "reduced", "end"};

@@ -144,7 +144,7 @@ struct PkSmem {
     const bf16** nwp;        // [L][2] attention_norm / ffn_norm weights of every layer
     bf16* nw;                // [<= 1536] the phase's RMSNorm weights, staged by cp.async while the CTA waits for its A packets
 };
-static_assert(sizeof(PkAttnPlan) <= 1024 && PKP_WARPS == PK_WARPS && PKP_MAXSEG == PK_MAXSEG && offsetof(PkAttnPlan, part) % 16 == 0 && offsetof(PkAttnPlan, hk) % 8 == 0, "plan layout");
+static_assert(sizeof(PkAttnPlan) <= 1024 && PKP_WARPS == PK_WARPS && PKP_MAXSEG == PK_MAXSEG, "plan layout");
 
 // ---------------------------------------------------------------------------------------------------------
 // weight stream: the producer thread walks the CTA's units in consumption order
@@ -579,8 +579,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         if (stamp && first) dbg[4] = pk_now();
         if (first) PK_W(10);
         // The batch's ring slots have been free since the barrier above: keep the weight stream ahead.  Issued AFTER this
-        // thread's share of the epilogue — the cursor walk (pointer-table loads, a few hundred instructions per unit) sat in
-        // front of the packet stores of the issuing warp and every consumer of those packets waited for it.
+        // thread's share of the epilogue, so the cursor walk does not sit in front of the issuing warp's packet stores.
         if (tid == PK_THREADS - 32) {
             PkStream& st = *sm.st;
             while (!st.c.done && st.issued < cons + PK_NSLOT) pk_stream_issue(P, sm, st);
@@ -600,7 +599,13 @@ __device__ __forceinline__ void pk_attn_finalize(const PkParams& P, float Mx, fl
                                                  int par) {
     const int first_cta = sgm.first_cta;
     uint2* pb = P.partial[par] + ((size_t)sgm.bh * P.part_slots) * 66;
-    // (owner segments only: a helper piece is published by pk_attn_phase right after its pass)
+    if (!sgm.owner) {
+        uint2* mine = pb + (size_t)((int)blockIdx.x - first_cta) * 66;
+        pk_st64(mine + 2 + e, __float_as_uint(a), tag);
+        if (e == 0) pk_st64(mine, __float_as_uint(Mx), tag);
+        if (e == 1) pk_st64(mine + 1, __float_as_uint(Ls), tag);
+        return;
+    }
     if (sgm.ks > 0) {   // combine the helpers' partials (CTAs first_cta .. blockIdx.x - 1) in index order, then ours
         const int nh = (int)blockIdx.x - first_cta;
         float Mc = -INFINITY, Lc = 0.f, ac = 0.f;
@@ -650,7 +655,7 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     const uint2* qkvb = P.qkv[par];
     const bf16* kc = sm.kvp[2 * layer];
     const bf16* vc = sm.kvp[2 * layer + 1];
-    float* sc = sm.red;                                    // [PK_WARPS][3][ENT]: pass 0 (helper piece), passes 1 / 2
+    float* sc = sm.red;                                    // [PK_WARPS][2][ENT]
 
     // q (and, for owner segments, this token's k and v) of every segment -> shared memory, polled in parallel:
     // warp sg, lanes 0-7 q, 8-15 k, 16-23 v (lane & 7 = 16-byte chunk = 4 packets)
@@ -673,42 +678,11 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     if (stamp) dbg[1] = pk_now();
     __syncthreads();                                       // q/k/v rows visible; the scratch aliases the previous phase's reduction buffer
 
-    // Pass 0 = the helper piece (keys of a pair whose owner is the next CTA), all 16 warps on it; its partial is published
-    // right after, so the owner finds it in L2 when it finishes its own keys.  Passes 1, 2 = the two parts of the warp's range
-    // of the owner segments.  One loop, one copy of the key-loop code (instruction cache).
-    const int has_h = pl.has_h;
 #pragma unroll 1
-    for (int part = has_h ? 0 : 1; part < 3; ++part) {
-        if (part == 1 && has_h) {
-            __syncthreads();                               // (CTA-uniform) the H entries are complete
-            if (warp < 2) {
-                const int e = tid & 63, hw1 = pl.h_w1;
-                float Mx = -INFINITY;
-                for (int w = 0; w <= hw1; ++w) Mx = fmaxf(Mx, sc[(w * 3) * ENT + 1]);
-                float Ls = 0.f, a = 0.f;
-                for (int w = 0; w <= hw1; ++w) {
-                    const float* en = sc + (w * 3) * ENT;
-                    const float mi = en[1];
-                    const float wt = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
-                    Ls += en[2] * wt;
-                    a += en[4 + e] * wt;
-                }
-                const PkSegPlan& hs = pl.seg[nseg - 1];
-                uint2* mine = P.partial[par] + ((size_t)hs.bh * P.part_slots + ((int)blockIdx.x - hs.first_cta)) * 66;
-                pk_st64(mine + 2 + e, __float_as_uint(a), tag);
-                if (e == 0) pk_st64(mine, __float_as_uint(Mx), tag);
-                if (e == 1) pk_st64(mine + 1, __float_as_uint(Ls), tag);
-            }
-        }
-        float* ent = sc + (size_t)(warp * 3 + part) * ENT;
-        int bh, b, k0, k1;
-        if (part == 0) {
-            const int2 hk = *reinterpret_cast<const int2*>(&pl.hk[warp][0]);
-            bh = pair_lo + nseg - 1; b = pl.seg[nseg - 1].b; k0 = hk.x; k1 = hk.y;
-        } else {
-            const int4 pt = *reinterpret_cast<const int4*>(&pl.part[warp][part - 1]);   // {bh, b, k0, k1}
-            bh = pt.x; b = pt.y; k0 = pt.z; k1 = pt.w;
-        }
+    for (int part = 0; part < 2; ++part) {
+        float* ent = sc + (size_t)(warp * 2 + part) * ENT;
+        const int4 pt = *reinterpret_cast<const int4*>(&pl.part[warp][part]);   // {bh, b, k0, k1}
+        const int bh = pt.x, b = pt.y, k0 = pt.z, k1 = pt.w;
         if (k0 >= k1) continue;                            // (warp-uniform)
         const int sg = bh - pair_lo;
         float qf[EPL];
@@ -812,15 +786,15 @@ __device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& s
     // warps whose range touches the pair are visited (a handful, not all 32 entries): this section runs on two warps alone.
     {
         const int sg = warp >> 1, e = tid & 63;
-        if (sg < nseg - has_h) {                           // owner segments (the helper piece was published after pass 0)
+        if (sg < nseg) {
             const PkSegPlan& q = pl.seg[sg];
             const int w0 = q.w0, w1 = q.w1;
             const unsigned int pm = q.part_mask;
             float Mx = -INFINITY;
-            for (int w = w0; w <= w1; ++w) Mx = fmaxf(Mx, sc[(w * 3 + 1 + (int)((pm >> w) & 1u)) * ENT + 1]);
+            for (int w = w0; w <= w1; ++w) Mx = fmaxf(Mx, sc[(w * 2 + (int)((pm >> w) & 1u)) * ENT + 1]);
             float Ls = 0.f, a = 0.f;
             for (int w = w0; w <= w1; ++w) {
-                const float* en = sc + (w * 3 + 1 + (int)((pm >> w) & 1u)) * ENT;
+                const float* en = sc + (w * 2 + (int)((pm >> w) & 1u)) * ENT;
                 const float mi = en[1];
                 const float wt = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
                 Ls += en[2] * wt;
@@ -955,7 +929,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
             const unsigned int tag = tag0 + (unsigned int)l;
             const int nph = l < P.L ? 5 : 1;
             for (int ph = 0; ph < nph; ++ph) {
-                long long* dbg = (dbg_step && l == 3) ? dbg_cta + 8 + 8 * ph : nullptr;
+                long long* dbg = (dbg_step && l == 3) ? dbg_cta + 8 + 8 * ph : (dbg_step && l == P.L) ? dbg_cta + 56 : nullptr;   // (head: slots 56 .. 60)
                 if (l < P.L && ph == 1) { pk_attn_phase(P, sm, l, p, tag, par, dbg); continue; }
                 const int kind = l == P.L ? 4 : (ph == 0 ? 0 : ph - 1);
                 pk_gemm_phase(P, sm, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg,

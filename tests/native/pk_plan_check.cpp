@@ -1,6 +1,5 @@
 // Host check of controlar_b200/csrc/pk_plan.h (the per-token attention work split of the persistent decode kernel):
-// the parts of all CTAs / warps must tile the flattened (pair, key) space exactly once, in order (per CTA: the owner range
-// [f0, fh) by `part`, then the helper piece [fh, f1) by `hk` — the kernel runs the helper piece FIRST), and the per-segment
+// the parts of all CTAs / warps must tile the flattened (pair, key) space exactly once, in order, and the per-segment
 // records (key range, owner, warp range, part mask, first CTA) must describe exactly those parts.
 // usage: pk_plan_check grid b_eff H n_lo n_hi   -> prints "ok <cases>" or the first violation, exit code 1
 #include <cstdio>
@@ -37,28 +36,6 @@ int main(int argc, char** argv) {
                     if ((long long)q.bh * n + q.k0 != cursor) FAIL("gap/overlap at w=%d p=%d: start %lld cursor %lld", w, p, (long long)q.bh * n + q.k0, cursor);
                     cursor = (long long)q.bh * n + q.k1;
                 }
-            // the helper piece: keys of the CTA's last pair, only when that pair's last key lies in a later CTA
-            {
-                const long long G0 = tot < grid ? tot : grid;
-                const long long f1 = (long long)(c + 1) * tot / G0;
-                const int pair_hi0 = (int)((f1 - 1) / n);
-                const bool helper = f1 < (long long)(pair_hi0 + 1) * n;
-                if ((pl.has_h != 0) != helper) FAIL("has_h %d", pl.has_h);
-                int last = -1;
-                for (int w = 0; w < PKP_WARPS; ++w) {
-                    const int k0 = pl.hk[w][0], k1 = pl.hk[w][1];
-                    if (k0 >= k1) continue;
-                    if (!helper) FAIL("H part without a helper piece");
-                    if (last != w - 1) FAIL("H parts must be the first warps, contiguous");
-                    last = w;
-                    if (k0 < 0 || k1 > n) FAIL("H range");
-                    if ((long long)pair_hi0 * n + k0 != cursor) FAIL("H gap/overlap at w=%d: start %lld cursor %lld", w, (long long)pair_hi0 * n + k0, cursor);
-                    cursor = (long long)pair_hi0 * n + k1;
-                }
-                if (helper && (last < 0 || pl.h_w1 != last)) FAIL("h_w1 %d vs %d", pl.h_w1, last);
-                if (helper && cursor != f1) FAIL("H coverage");
-                if (helper && cursor >= (long long)(pair_hi0 + 1) * n) FAIL("helper piece holds the last key");
-            }
             // CTA ranges are balanced: floor((c+1) tot / G) boundaries
             const long long G = tot < grid ? tot : grid;
             if (c_start != (long long)c * tot / G || cursor != (long long)(c + 1) * tot / G) FAIL("cta range");
@@ -70,16 +47,6 @@ int main(int argc, char** argv) {
                 const PkSegPlan& g = pl.seg[s];
                 if (g.bh != pair_lo + s || g.b != g.bh / H || g.hd != g.bh % H) FAIL("seg ids");
                 int kmin = 1 << 30, kmax = -1;
-                if (pl.has_h && s == pl.nseg - 1) {           // the helper piece is described by hk, not by part
-                    for (int w = 0; w < PKP_WARPS; ++w) {
-                        const int k0 = pl.hk[w][0], k1 = pl.hk[w][1];
-                        const bool in = w >= g.w0 && w <= g.w1;
-                        if ((k0 < k1) != in) FAIL("helper seg warp %d", w);
-                        if (k0 < k1) { if (k0 < kmin) kmin = k0; if (k1 > kmax) kmax = k1; }
-                        for (int p = 0; p < 2; ++p) if (pl.part[w][p].k0 < pl.part[w][p].k1 && pl.part[w][p].bh == g.bh) FAIL("O part inside the helper pair");
-                    }
-                    if (g.owner) FAIL("helper piece marked owner");
-                } else
                 for (int w = 0; w < PKP_WARPS; ++w) {
                     int hits = 0, which = -1;
                     for (int p = 0; p < 2; ++p) {
