@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
             a.h_out = nullptr; a.tok_buf = nullptr;
             a.dbg_ts = (dbg_step && blockIdx.x == 0) ? dbg_cta + 48 : nullptr;   // (slots 8 .. 47: the five phases of layer 3)
             static_assert(SMP_SCRATCH <= PK_SMEM_RED, "the sampler's scratch aliases the reduction buffer");
-            sample_body<PK_THREADS, 32>(a, blockIdx.x, reinterpret_cast<unsigned char*>(sm.red));
+            sample_body<PK_THREADS>(a, blockIdx.x, reinterpret_cast<unsigned char*>(sm.red));
             __syncthreads();
             if (tid == 0) s_tok = P.forced != nullptr ? __ldg(P.forced + (size_t)blockIdx.x * P.forced_ld + step)
                                                       : ld_cg(a.idx_out + (size_t)blockIdx.x * a.tokens_ld + step);

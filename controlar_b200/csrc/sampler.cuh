@@ -96,17 +96,9 @@ __device__ __forceinline__ void write_next_h(const SampleArgs& a, int b_row, int
     }
 }
 
-// Block-wide deterministic reductions (fixed tree): `red` holds THREADS/32 slots.
-template <int THREADS> __device__ __forceinline__ float smp_block_sum(float v, float* red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) s += red[w];
-    return s;
-}
+// Block-wide reductions; `red` holds THREADS/32 slots.  max / count are order-independent; the soft-max mass is accumulated in
+// 64-bit fixed point (2^-40 units), which is associative — so the result does not depend on the order in which the kept elements
+// were compacted, and two runs give identical tokens.
 template <int THREADS> __device__ __forceinline__ float smp_block_max(float v, float* red) {
     v = warp_max(v);
     __syncthreads();
@@ -117,103 +109,146 @@ template <int THREADS> __device__ __forceinline__ float smp_block_max(float v, f
     for (int w = 1; w < THREADS / 32; ++w) s = fmaxf(s, red[w]);
     return s;
 }
-template <int THREADS> __device__ __forceinline__ unsigned smp_block_count(unsigned v, unsigned* red) {
-    v = __reduce_add_sync(0xffffffffu, v);
+template <int THREADS> __device__ __forceinline__ unsigned long long smp_block_sum64(unsigned long long v, unsigned long long* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    unsigned s = 0;
+    unsigned long long s = 0ull;
 #pragma unroll
     for (int w = 0; w < THREADS / 32; ++w) s += red[w];
     return s;
 }
+template <int THREADS> __device__ __forceinline__ void smp_block_count3(unsigned& c1, unsigned& c2, unsigned& c3, unsigned (*red)[3]) {
+    c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = c1; red[threadIdx.x >> 5][1] = c2; red[threadIdx.x >> 5][2] = c3; }
+    __syncthreads();
+    c1 = c2 = c3 = 0u;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) { c1 += red[w][0]; c2 += red[w][1]; c3 += red[w][2]; }
+}
 
-// One CTA per image (b).  The row lives in registers: thread t owns elements t, t+THREADS, ... (EPT of them).
-//   top-k : exact k-th largest by a two-level selection (2048-bin histogram over a monotone linear map of the values, then exact
-//           ranks of the few candidates of the boundary bin on the order-preserving integer keys); ties at the threshold are kept
-//   soft-max / nucleus / race only touch the kept elements (k of V), Philox is evaluated per kept element.
+// shared scratch of sample_body: selection histogram | boundary-bin candidates (index, value) | compacted kept list (index, value)
+constexpr int SMP_NBIN = 2048, SMP_NCAND = 1024, SMP_CAP = 2304;        // CAP: top_k <= 2000 plus ties at the threshold
+constexpr int SMP_SCRATCH = SMP_NBIN * 4 + SMP_NCAND * 8 + SMP_CAP * 8;
+constexpr float SMP_FIX = 1099511627776.0f;                              // 2^40: fixed-point unit of the soft-max mass
+
+// four consecutive elements of the CFG-combined, temperature-scaled row (generate.py:103-107, :60); separate sub / mul / add like
+// the eager reference (no FMA contraction), identical bits in every pass over the row
+__device__ __forceinline__ float4 smp_z4(const SampleArgs& a, const float* lc, const float* lu, int i4, bool cfg) {
+    float4 v = __ldcg(reinterpret_cast<const float4*>(lc) + i4);
+    if (cfg) {
+        const float4 u = __ldcg(reinterpret_cast<const float4*>(lu) + i4);
+        v.x = __fadd_rn(u.x, __fmul_rn(__fsub_rn(v.x, u.x), a.cfg_scale)); v.y = __fadd_rn(u.y, __fmul_rn(__fsub_rn(v.y, u.y), a.cfg_scale));
+        v.z = __fadd_rn(u.z, __fmul_rn(__fsub_rn(v.z, u.z), a.cfg_scale)); v.w = __fadd_rn(u.w, __fmul_rn(__fsub_rn(v.w, u.w), a.cfg_scale));
+    }
+    v.x = __fmul_rn(v.x, a.inv_temp); v.y = __fmul_rn(v.y, a.inv_temp); v.z = __fmul_rn(v.z, a.inv_temp); v.w = __fmul_rn(v.w, a.inv_temp);
+    return v;
+}
+
+// One CTA per image (b).  Nothing of the row is kept in registers: every stage is a short rolled loop, either over the row itself
+// (re-read from L2 and re-combined: 2 x 64 KB per pass) or over the compacted list of kept elements in shared memory.  (The
+// register-resident version was 8 K fully unrolled instructions executed once per token — in the persistent decode kernel that
+// is 130 KB of cold instruction fetch per token, and its per-element shared-memory atomics serialised: 49 us per token.)
+//   top-k : exact k-th largest by a two-level selection — a 2048-bin histogram over a monotone linear map of the value range, then
+//           exact ranks of the few candidates of the boundary bin on the order-preserving integer keys; ties at the threshold are
+//           kept (generate.py:37).  Crowded boundary bin (degenerate rows): bit-wise bisection over the row, two bits per pass.
+//   kept  : elements above the boundary bin + the candidates at or above the threshold, compacted into shared memory (<= SMP_CAP
+//           entries; larger kept sets — top_k = 0 or huge — run the same stages as passes over the row instead).
+//   soft-max / nucleus / exponential race touch the kept elements only; Philox is evaluated per kept element.
 #ifdef PK_TRACE
 #define SMP_STAMP(k) do { if (a.dbg_ts != nullptr && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.dbg_ts[k] = t_; } } while (0)
 #else
 #define SMP_STAMP(k) do { } while (0)
 #endif
 
-constexpr int SMP_SCRATCH = 2304 * 8;     // bytes of shared scratch sample_body needs (selection histogram + candidates, later the compacted race list)
+// visit every kept element (index, value): the compacted list, or the whole row filtered by the threshold key
+template <int THREADS, typename F>
+__device__ __forceinline__ void smp_for_kept(const SampleArgs& a, const float* lc, const float* lu, bool cfg, bool use_list, const int* ki,
+                                             const float* kz, unsigned nk, bool has_thr, unsigned thr, F f) {
+    if (use_list) {
+        for (unsigned c = threadIdx.x; c < nk; c += THREADS) f(ki[c], kz[c]);
+    } else {
+        const int V4 = a.V >> 2;
+#pragma unroll 2
+        for (int i4 = threadIdx.x; i4 < V4; i4 += THREADS) {
+            const float4 z = smp_z4(a, lc, lu, i4, cfg);
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (!has_thr || float_order_key(zz[q]) >= thr) f(4 * i4 + q, zz[q]);
+        }
+    }
+}
 
-template <int THREADS, int EPT>
+template <int THREADS>
 __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, unsigned char* scratch) {
-    __shared__ float red_f[THREADS / 32];
-    __shared__ unsigned red_u[THREADS / 32];
-    __shared__ int red_i[THREADS / 32];
+    constexpr int NW = THREADS / 32;
+    __shared__ float red_f[NW];
+    __shared__ unsigned long long red_q[NW];
+    __shared__ unsigned red_u[NW];
+    __shared__ unsigned red_c[NW][3];
+    __shared__ int red_i[NW];
     __shared__ int s_tok;
+    __shared__ unsigned s_cnt, s_nk, s_bin, s_krem, s_thr, s_over;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int V = a.V;
+    const int V = a.V, V4 = V >> 2;                        // (host-checked: V % 4 == 0)
     const int pos = a.pos_ptr ? ld_cg(a.pos_ptr) : a.pos_val;
     const int step = a.pos_ptr ? (pos - a.T + 1) : a.step;   // index of the token being produced
     bool cfg_on = a.cfg_on != 0;
     if (a.cfg_interval > -1 && step - 1 > a.cfg_interval) cfg_on = false;
-
-    SMP_STAMP(0);
-    // ---- CFG combine + temperature (generate.py:103-107, :60)
-    float zr[EPT];
+    const bool cfg = a.use_cfg && cfg_on;
     const float* lc = a.logits + (size_t)b * V;
     const float* lu = a.logits + (size_t)(b + a.B) * V;
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int i = tid + j * THREADS;
-        float v = -INFINITY;
-        if (i < V) {
-            v = __ldcg(lc + i);
-            if (a.use_cfg && cfg_on) { const float u = __ldcg(lu + i); v = u + (v - u) * a.cfg_scale; }
-            v *= a.inv_temp;
-        }
-        zr[j] = v;
-    }
-    SMP_STAMP(1);
-    // ---- top-k threshold (ties at the threshold are kept, generate.py:37).  The row is turned into its order-preserving
-    // integer keys in place (the map is a bijection), bisected, and turned back — one register array, not two.
-    if (a.top_k > 0 && a.top_k < V) {
-        // Exact radix-style selection in two levels.  Level 1: a 2048-bin histogram over a MONOTONE linear map of the value range
-        // (bin = int((z - lo) * scale): rounding, scaling and truncation are all monotone, so every element of a higher bin is
-        // strictly larger than every element of a lower one; linear bins spread a bell-shaped row over ~all bins, where bins
-        // on the raw float bits would pile it into a handful and serialise the shared-memory atomics).  Level 2: the bin that
-        // contains the k-th largest element holds a few dozen candidates; their exact rank is counted on the order-preserving
-        // integer keys.  Falls back to the bit-wise bisection when that bin is crowded (degenerate rows).
-        constexpr int NBIN = 2048, BPT = NBIN / THREADS, NCAND = 1024;
-        static_assert(NBIN % THREADS == 0, "bins per thread");
-        static_assert((NBIN + NCAND) * 4 <= SMP_SCRATCH, "selection scratch");
-        unsigned* const s_hist = reinterpret_cast<unsigned*>(scratch);
-        unsigned* const s_cand = s_hist + NBIN;
-        __shared__ unsigned s_cnt, s_bin, s_krem, s_thr;
+    unsigned* const s_hist = reinterpret_cast<unsigned*>(scratch);
+    int* const s_ci = reinterpret_cast<int*>(scratch + SMP_NBIN * 4);
+    float* const s_cz = reinterpret_cast<float*>(scratch + SMP_NBIN * 4 + SMP_NCAND * 4);
+    int* const s_ki = reinterpret_cast<int*>(scratch + SMP_NBIN * 4 + SMP_NCAND * 8);
+    float* const s_kz = reinterpret_cast<float*>(scratch + SMP_NBIN * 4 + SMP_NCAND * 8 + SMP_CAP * 4);
+
+    SMP_STAMP(0);
+    const bool has_thr = a.top_k > 0 && a.top_k < V;
+    bool use_list = has_thr && a.top_k + 64 <= SMP_CAP;   // room for ties at the threshold; else the stages run over the row
+    unsigned thr = 0u, nk = 0u;
+    if (has_thr) {
+        // ---- level 1: value range, histogram, boundary bin
         float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) if (tid + j * THREADS < V) { lo = fminf(lo, zr[j]); hi = fmaxf(hi, zr[j]); }
+#pragma unroll 2
+        for (int i4 = tid; i4 < V4; i4 += THREADS) {
+            const float4 z = smp_z4(a, lc, lu, i4, cfg);
+            lo = fminf(fminf(lo, z.x), fminf(z.y, fminf(z.z, z.w)));
+            hi = fmaxf(fmaxf(hi, z.x), fmaxf(z.y, fmaxf(z.z, z.w)));
+        }
         hi = smp_block_max<THREADS>(hi, red_f);
         lo = -smp_block_max<THREADS>(-lo, red_f);
-        const float scale = hi > lo ? (float)(NBIN - 1) / (hi - lo) : 0.f;
-#pragma unroll
-        for (int i = 0; i < BPT; ++i) s_hist[tid * BPT + i] = 0u;
-        if (tid == 0) { s_cnt = 0u; s_thr = 0u; }
+        const float scale = (hi > lo && lo > -INFINITY) ? (float)(SMP_NBIN - 1) / (hi - lo) : 0.f;
+        for (int i = tid; i < SMP_NBIN; i += THREADS) s_hist[i] = 0u;
+        if (tid == 0) { s_cnt = 0u; s_nk = 0u; s_thr = 0u; s_over = 0u; s_bin = 0u; s_krem = (unsigned)a.top_k; }
         __syncthreads();
-        int mybin[EPT];
+        SMP_STAMP(1);
+#pragma unroll 2
+        for (int i4 = tid; i4 < V4; i4 += THREADS) {
+            const float4 z = smp_z4(a, lc, lu, i4, cfg);
+            const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            mybin[j] = min(max((int)((zr[j] - lo) * scale), 0), NBIN - 1);
-            if (tid + j * THREADS < V) atomicAdd(&s_hist[mybin[j]], 1u);
+            for (int q = 0; q < 4; ++q) atomicAdd(&s_hist[min(max((int)((zz[q] - lo) * scale), 0), SMP_NBIN - 1)], 1u);
         }
         __syncthreads();
         SMP_STAMP(5);
-        {   // bin (from the top) in which the cumulative count reaches k
+        {   // bin (from the top) in which the cumulative count reaches k: thread t owns bins [t BPT, (t + 1) BPT)
+            constexpr int BPT = (SMP_NBIN + THREADS - 1) / THREADS;
             unsigned loc[BPT], mine = 0u;
 #pragma unroll
-            for (int i = 0; i < BPT; ++i) { loc[i] = s_hist[tid * BPT + i]; mine += loc[i]; }
+            for (int i = 0; i < BPT; ++i) { const int bi = tid * BPT + i; loc[i] = bi < SMP_NBIN ? s_hist[bi] : 0u; mine += loc[i]; }
             unsigned incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += v; }
             if (lane == 0) red_u[warp] = incl;
             __syncthreads();
             unsigned above = incl - mine;
-            for (int w = warp + 1; w < THREADS / 32; ++w) above += red_u[w];
+            for (int w = warp + 1; w < NW; ++w) above += red_u[w];
             const unsigned kk = (unsigned)a.top_k;
 #pragma unroll
             for (int i = BPT - 1; i >= 0; --i) {
@@ -225,151 +260,135 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
         SMP_STAMP(6);
         const int bsel = (int)s_bin;
         const unsigned krem = s_krem;
+        // ---- level 2: one pass collects the elements above the boundary bin (kept for sure) and the boundary bin's candidates
+#pragma unroll 2
+        for (int i0 = 0; i0 < V4; i0 += THREADS) {         // (warp-uniform trip count: the allocation below uses warp collectives)
+            const int i4 = i0 + tid;
+            const bool valid = i4 < V4;
+            const float4 z = smp_z4(a, lc, lu, valid ? i4 : 0, cfg);
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+            int bin[4];
+            unsigned mykeep = 0u;
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            if (tid + j * THREADS < V && mybin[j] == bsel) {
-                const unsigned pc = atomicAdd(&s_cnt, 1u);
-                if (pc < (unsigned)NCAND) s_cand[pc] = float_order_key(zr[j]);
+            for (int q = 0; q < 4; ++q) {
+                bin[q] = valid ? min(max((int)((zz[q] - lo) * scale), 0), SMP_NBIN - 1) : -1;
+                mykeep += bin[q] > bsel ? 1u : 0u;
+                if (bin[q] == bsel) {
+                    const unsigned pc = atomicAdd(&s_cnt, 1u);
+                    if (pc < (unsigned)SMP_NCAND) { s_ci[pc] = 4 * i4 + q; s_cz[pc] = zz[q]; }
+                }
+            }
+            if (use_list) {                                // warp-aggregated allocation: one shared-memory atomic per warp and iteration
+                unsigned incl = mykeep;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned base = 0u;
+                if (tot != 0u) {
+                    if (lane == 31) base = atomicAdd(&s_nk, tot);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    unsigned at = base + incl - mykeep;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (bin[q] > bsel) { if (at < (unsigned)SMP_CAP) { s_ki[at] = 4 * i4 + q; s_kz[at] = zz[q]; } ++at; }
+                }
             }
         }
         __syncthreads();
         SMP_STAMP(7);
         const unsigned ncand = s_cnt;
-        unsigned cand = 0u;
-        if (ncand <= (unsigned)NCAND) {
+        if (ncand <= (unsigned)SMP_NCAND) {
             // exact rank inside the bin: the k_rem-th largest candidate (duplicates counted) is the one with
             // #{greater} < k_rem <= #{greater or equal}
             for (unsigned c = tid; c < ncand; c += THREADS) {
-                const unsigned key = s_cand[c];
+                const unsigned key = float_order_key(s_cz[c]);
                 unsigned gt = 0u, ge = 0u;
-                for (unsigned q = 0; q < ncand; ++q) { const unsigned kq = s_cand[q]; gt += kq > key ? 1u : 0u; ge += kq >= key ? 1u : 0u; }
+                for (unsigned q = 0; q < ncand; ++q) { const unsigned kq = float_order_key(s_cz[q]); gt += kq > key ? 1u : 0u; ge += kq >= key ? 1u : 0u; }
                 if (gt < krem && krem <= ge) s_thr = key;                  // (ties write the same value)
             }
             __syncthreads();
-            cand = s_thr;
-        } else {
-            // crowded bin: bit-wise bisection on the integer keys of the whole row, two bits per step
-            __shared__ unsigned red_c[2][THREADS / 32][3];
-#pragma unroll 1
-            for (int shift = 30, it = 0; shift >= 0; shift -= 2, ++it) {
-                const unsigned t1 = cand | (1u << shift), t2 = cand | (2u << shift), t3 = cand | (3u << shift);
-                unsigned c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) {
-                    const unsigned k = (tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u;
-                    c1 += k >= t1 ? 1u : 0u; c2 += k >= t2 ? 1u : 0u; c3 += k >= t3 ? 1u : 0u;
-                }
-                c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
-                if (lane == 0) { red_c[it & 1][warp][0] = c1; red_c[it & 1][warp][1] = c2; red_c[it & 1][warp][2] = c3; }
+            thr = s_thr;
+            if (use_list) {                                // candidates at or above the threshold join the kept list
+                for (unsigned c = tid; c < ncand; c += THREADS)
+                    if (float_order_key(s_cz[c]) >= thr) {
+                        const unsigned at = atomicAdd(&s_nk, 1u);
+                        if (at < (unsigned)SMP_CAP) { s_ki[at] = s_ci[c]; s_kz[at] = s_cz[c]; }
+                    }
                 __syncthreads();
-                unsigned s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-                for (int w = 0; w < THREADS / 32; ++w) { s1 += red_c[it & 1][w][0]; s2 += red_c[it & 1][w][1]; s3 += red_c[it & 1][w][2]; }
-                const unsigned kk = (unsigned)a.top_k;                 // counts are non-increasing in the threshold
-                cand = s3 >= kk ? t3 : (s2 >= kk ? t2 : (s1 >= kk ? t1 : cand));
             }
-        }
+        } else {
+            // crowded bin: bit-wise bisection on the integer keys of the whole row, two bits per pass
+#pragma unroll 1
+            for (int shift = 30; shift >= 0; shift -= 2) {
+                const unsigned t1 = thr | (1u << shift), t2 = thr | (2u << shift), t3 = thr | (3u << shift);
+                unsigned c1 = 0, c2 = 0, c3 = 0;
+                for (int i4 = tid; i4 < V4; i4 += THREADS) {
+                    const float4 z = smp_z4(a, lc, lu, i4, cfg);
+                    const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const unsigned key = (tid + j * THREADS) < V ? float_order_key(zr[j]) : 0u;
-            if (key < cand) zr[j] = -INFINITY;
+                    for (int q = 0; q < 4; ++q) { const unsigned k = float_order_key(zz[q]); c1 += k >= t1 ? 1u : 0u; c2 += k >= t2 ? 1u : 0u; c3 += k >= t3 ? 1u : 0u; }
+                }
+                smp_block_count3<THREADS>(c1, c2, c3, red_c);
+                const unsigned kk = (unsigned)a.top_k;                 // counts are non-increasing in the threshold
+                thr = c3 >= kk ? t3 : (c2 >= kk ? t2 : (c1 >= kk ? t1 : thr));
+            }
+            use_list = false;                              // (the list holds only the bins above; this rare path runs over the row)
         }
+        nk = s_nk;
+        if (nk > (unsigned)SMP_CAP) use_list = false;      // (CTA-uniform) more ties than the list holds
     }
     SMP_STAMP(2);
+    auto for_kept = [&](auto f) { smp_for_kept<THREADS>(a, lc, lu, cfg, use_list, s_ki, s_kz, nk, has_thr, thr, f); };
+
     // ---- soft-max over the kept elements
     float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) mx = fmaxf(mx, zr[j]);
+    for_kept([&](int, float z) { mx = fmaxf(mx, z); });
     mx = smp_block_max<THREADS>(mx, red_f);
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const float e = zr[j] == -INFINITY ? 0.f : expf(zr[j] - mx);
-        zr[j] = e;
-        sum += e;
-    }
-    sum = smp_block_sum<THREADS>(sum, red_f);
+    unsigned long long mass = 0ull;
+    for_kept([&](int, float z) { mass += __float2ull_rn(expf(z - mx) * SMP_FIX); });
+    mass = smp_block_sum64<THREADS>(mass, red_q);
+    float sum = (float)mass * (1.0f / SMP_FIX);
     // ---- nucleus (top-p), generate.py:40-55: in descending order a token is removed iff the cumulative probability
     // of the tokens strictly before it exceeds top_p (first always kept).  Equivalently token x is kept iff
     // f(p_x) <= top_p with f(v) = mass of tokens with probability > v; f is a non-increasing step function, so the
     // kept set is {p >= tau*}; tau* is bracketed by 30 bisection steps (tokens within 2^-30 of the boundary count as
     // ties and are kept; torch.sort's order among exact ties is unspecified anyway).
+    const float sum_pre = sum;                             // normaliser of the pre-nucleus probabilities
+    float p_lo = -1.f;                                     // elements with pre-nucleus probability <= p_lo are dropped (none by default)
     if (a.top_p < 1.0f) {
-        float lo = 0.f, hi = 1.0f;                       // f(lo) > top_p >= f(hi)
+        float lo = 0.f, hi = 1.0f;                         // f(lo) > top_p >= f(hi)
+        const double budget = (double)a.top_p * (double)mass;
         for (int it = 0; it < 30; ++it) {
             const float mid = 0.5f * (lo + hi);
-            float ma = 0.f;
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) { const float p = zr[j] / sum; if (p > mid) ma += p; }
-            ma = smp_block_sum<THREADS>(ma, red_f);
-            if (ma <= a.top_p) hi = mid; else lo = mid;
+            unsigned long long ma = 0ull;
+            for_kept([&](int, float z) { const float e = expf(z - mx); if (e / sum_pre > mid) ma += __float2ull_rn(e * SMP_FIX); });
+            ma = smp_block_sum64<THREADS>(ma, red_q);
+            if ((double)ma <= budget) hi = mid; else lo = mid;
         }
-        float s2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) { if (!(zr[j] / sum > lo)) zr[j] = 0.f; s2 += zr[j]; }
-        sum = smp_block_sum<THREADS>(s2, red_f);         // soft-max over the kept logits only
+        p_lo = lo;
+        unsigned long long m2 = 0ull;
+        for_kept([&](int, float z) { const float e = expf(z - mx); if (e / sum_pre > p_lo) m2 += __float2ull_rn(e * SMP_FIX); });
+        m2 = smp_block_sum64<THREADS>(m2, red_q);
+        sum = (float)m2 * (1.0f / SMP_FIX);                // soft-max over the surviving logits only
     }
     if (a.probs_out) {
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) { const int i = tid + j * THREADS; if (i < V) a.probs_out[(size_t)b * V + i] = zr[j] / sum; }
+        float* po = a.probs_out + (size_t)b * V;
+        for (int i4 = tid; i4 < V4; i4 += THREADS) reinterpret_cast<float4*>(po)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        for_kept([&](int i, float z) { const float e = expf(z - mx); if (e / sum_pre > p_lo) po[i] = e / sum; });
     }
     SMP_STAMP(3);
     // ---- draw: arg-max of p (greedy) or of p / q (exponential race); lowest index wins ties
     float best = -1.f; int besti = 0x7fffffff;
     const float* nz = a.noise ? a.noise + ((size_t)(a.noise_per_step ? step : 0) * a.B + b) * V : nullptr;
-    bool raced = false;
-    if (a.sample_logits && nz == nullptr) {
-        // Philox costs ~100 instructions per element and the kept elements (top_k of V) are scattered over all lanes, so the
-        // element-order loop below would run the generator in every (warp, j) iteration for a few lanes each.  Compact the
-        // kept (index, probability) pairs into shared memory first and race over the dense list: the arg-max with the
-        // lowest-index tie-break does not depend on the order, so the token is the same one.
-        constexpr int CAP = 2304;                       // top_k <= 2000 plus ties; larger kept sets take the plain loop
-        static_assert(CAP * 8 <= SMP_SCRATCH, "race list scratch");
-        int* const s_ci = reinterpret_cast<int*>(scratch);               // (the selection scratch is dead: block reductions lie in between)
-        float* const s_cp = reinterpret_cast<float*>(scratch + CAP * 4);
-        __shared__ unsigned s_cn;
-        if (tid == 0) s_cn = 0u;
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int i = tid + j * THREADS;
-            const bool kept = i < V && zr[j] > 0.f;
-            const unsigned bal = __ballot_sync(0xffffffffu, kept);
-            if (bal != 0u) {                            // (warp-uniform)
-                unsigned base = 0u;
-                if (lane == 0) base = atomicAdd(&s_cn, (unsigned)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned at = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
-                if (kept && at < (unsigned)CAP) { s_ci[at] = i; s_cp[at] = zr[j] / sum; }
-            }
+    for_kept([&](int i, float z) {
+        const float e = expf(z - mx);
+        if (e / sum_pre > p_lo && e > 0.f) {
+            float sv = e / sum;
+            if (a.sample_logits) sv = sv / (nz ? nz[i] : exp1_noise(a.seed_lo, a.seed_hi, i, b, step));
+            if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
         }
-        __syncthreads();
-        const unsigned nk = s_cn;
-        if (nk <= (unsigned)CAP) {                      // (CTA-uniform)
-            raced = true;
-            for (unsigned c = tid; c < nk; c += THREADS) {
-                const int i = s_ci[c];
-                const float sv = s_cp[c] / exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
-                if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
-            }
-        }
-    }
-    if (!raced) {
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int i = tid + j * THREADS;
-            if (i < V && zr[j] > 0.f) {
-                float sv = zr[j] / sum;
-                if (a.sample_logits) {
-                    float q;
-                    if (nz) q = nz[i];
-                    else q = exp1_noise(a.seed_lo, a.seed_hi, i, b, step);
-                    sv = sv / q;
-                }
-                if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
-            }
-        }
-    }
+    });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -381,7 +400,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
     __syncthreads();
     if (tid == 0) {
         float bb = red_f[0]; int bi = red_i[0];
-        for (int w = 1; w < THREADS / 32; ++w)
+        for (int w = 1; w < NW; ++w)
             if (red_f[w] > bb || (red_f[w] == bb && red_i[w] < bi)) { bb = red_f[w]; bi = red_i[w]; }
         s_tok = bi;
         if (a.tokens_ld > 0) a.idx_out[(size_t)b * a.tokens_ld + step] = bi;
@@ -416,8 +435,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
     }
 }
 
-constexpr int SMP_EPT = 16;                       // V <= SMP_THREADS * SMP_EPT = 16384
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs a) {
     __shared__ __align__(16) unsigned char smp_scratch[SMP_SCRATCH];
-    sample_body<SMP_THREADS, SMP_EPT>(a, blockIdx.x, smp_scratch);
+    sample_body<SMP_THREADS>(a, blockIdx.x, smp_scratch);
 }
