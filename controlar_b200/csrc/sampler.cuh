@@ -172,11 +172,11 @@ __device__ __forceinline__ void smp_for_kept(const SampleArgs& a, const float* l
         for (unsigned c = threadIdx.x; c < nk; c += THREADS) f(ki[c], kz[c]);
     } else {
         const int V4 = a.V >> 2;
-#pragma unroll 2
-        for (int i4 = threadIdx.x; i4 < V4; i4 += THREADS) {
+#pragma unroll 1
+        for (int i4 = threadIdx.x; i4 < V4; i4 += THREADS) {   // (rare path: kept small, not fast)
             const float4 z = smp_z4(a, lc, lu, i4, cfg);
             const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 4; ++q)
                 if (!has_thr || float_order_key(zz[q]) >= thr) f(4 * i4 + q, zz[q]);
         }
