@@ -709,11 +709,6 @@ static int fill_sample_args(SampleArgs& a, const CarSampling* sp, int b_eff, int
 }
 
 static int launch_sampler(const SampleArgs& a, cudaStream_t st) {
-    static DevOnce once;
-    if (once.first()) {
-        CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CAR_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
     if (a.V % 4 != 0 || a.V < 4) CAR_FAIL(CAR_ERR_UNSUPPORTED, "the fused sampler needs a vocabulary size that is a multiple of 4");
     CAR_LAUNCH(sample_kernel, a.B, SMP_THREADS, 0, st, a);
     return CAR_OK;

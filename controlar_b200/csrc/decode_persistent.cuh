@@ -339,6 +339,17 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         }
     }
 
+    // qkv epilogue: section / head / element of this thread's column pair and its RoPE (cos, sin) — the 64-bit-free division and the
+    // table load (an L2 round trip) are taken off the path between the reduction and the packet stores
+    int q_col = 0;                                         // sec << 16 | head << 6 | el (one register across the poll and the MMA)
+    float2 q_cs = make_float2(1.f, 0.f);
+    if (kind == 0 && er == 0 && blk_lo + ej < blk_hi) {
+        const int n = (blk_lo + ej) * 8 + 2 * ecp;
+        const int sec = n / P.dim, w = n - sec * P.dim;
+        q_col = (sec << 16) | w;
+        if (sec < 2) q_cs = __ldg(reinterpret_cast<const float2*>(P.rope + ((size_t)pos * 32 + ((w & 63) >> 1)) * 2));
+    }
+
     if (NORM) {   // this phase's RMSNorm weights -> shared memory, asynchronously, while we wait for the A packets
         const bf16* nwg = kind == 0 ? sm.nwp[2 * l] : kind == 2 ? sm.nwp[2 * l + 1] : P.norm_w;
         if (tid < (K >> 3))
@@ -492,6 +503,10 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         if (stamp && first) dbg[3] = pk_now();
         if (first) PK_W(8);
         cons += nunits;
+        if (tid == PK_THREADS - 32) {                  // the batch's slots are free again: keep the stream ahead.  (Issuing after this
+            PkStream& st = *sm.st;                     // warp's epilogue instead was measured 2 us per layer SLOWER: the weight stream
+            while (!st.c.done && st.issued < cons + PK_NSLOT) pk_stream_issue(P, sm, st);   // falls behind, r2 GPU calls 2 / 3)
+        }
         {
             const int bb = b0, cnt = nb;
    // blocks bb .. bb + cnt - 1 are in the reduction buffer
@@ -521,11 +536,17 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
             if (active && er == 0) {
                 const int r_lo = eg, r_hi = eg + 8;
                 if (kind == 0) {
-                    const int n = (bb + ej) * 8 + 2 * ecp;
-                    const int sec = n / P.dim, w = n - sec * P.dim, head = w >> 6, el = w & 63;
+                    int sec = q_col >> 16, head = (q_col & 0xffff) >> 6, el = q_col & 63;
+                    float2 cs2 = q_cs;
+                    if (bb != blk_lo) {   // later batches (only models with more than 4 qkv blocks per CTA): recompute
+                        const int n = (bb + ej) * 8 + 2 * ecp;
+                        sec = n / P.dim;
+                        const int w = n - sec * P.dim;
+                        head = w >> 6; el = w & 63;
+                        if (sec < 2) cs2 = __ldg(reinterpret_cast<const float2*>(P.rope + ((size_t)pos * 32 + (el >> 1)) * 2));
+                    }
                     float a0 = rnd<bf16>(v00), a1 = rnd<bf16>(v01), c0 = rnd<bf16>(v10), c1 = rnd<bf16>(v11);
                     if (sec < 2) {   // apply_rotary_emb gpt_t2i.py:522-532 (interleaved pairs, fp32, then cast)
-                        const float2 cs2 = __ldg(reinterpret_cast<const float2*>(P.rope + ((size_t)pos * 32 + (el >> 1)) * 2));
                         const float x0 = a0 * cs2.x - a1 * cs2.y, x1 = a1 * cs2.x + a0 * cs2.y;
                         const float y0 = c0 * cs2.x - c1 * cs2.y, y1 = c1 * cs2.x + c0 * cs2.y;
                         a0 = x0; a1 = x1; c0 = y0; c1 = y1;
@@ -578,12 +599,6 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         }
         if (stamp && first) dbg[4] = pk_now();
         if (first) PK_W(10);
-        // The batch's ring slots have been free since the barrier above: keep the weight stream ahead.  Issued AFTER this
-        // thread's share of the epilogue, so the cursor walk does not sit in front of the issuing warp's packet stores.
-        if (tid == PK_THREADS - 32) {
-            PkStream& st = *sm.st;
-            while (!st.c.done && st.issued < cons + PK_NSLOT) pk_stream_issue(P, sm, st);
-        }
         b0 += nb;
         first = false;
     }
