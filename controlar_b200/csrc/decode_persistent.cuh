@@ -884,9 +884,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
         st.issued = 0;
         pk_cursor_skip_empty(P, st, st.c);
         st.pf = st.c;
-        if (P.exp_flags & 16) for (int i = 0; i < PK_NSLOT + PK_L2_AHEAD; ++i) pk_stream_prefetch(P, st);     // (the ring's first units included)
+        const int ahead = ((P.exp_flags >> 12) & 15) ? 2 * ((P.exp_flags >> 12) & 15) : PK_L2_AHEAD;   // (experiment knob: CAR_EXP bits 12-15)
+        if (P.exp_flags & 16) for (int i = 0; i < PK_NSLOT + ahead; ++i) pk_stream_prefetch(P, st);     // (the ring's first units included)
         st.pf = st.c;
-        { uint32_t b; for (int i = 0; i < PK_NSLOT + PK_L2_AHEAD && !st.pf.done; ++i) pk_cursor_take(P, st, st.pf, b); }
+        { uint32_t b; for (int i = 0; i < PK_NSLOT + ahead && !st.pf.done; ++i) pk_cursor_take(P, st, st.pf, b); }
         while (!st.c.done && st.issued < PK_NSLOT) { /* ring priming: no extra prefetch per unit yet */
             uint32_t bytes;
             const uint4* src = pk_cursor_take(P, st, st.c, bytes);
