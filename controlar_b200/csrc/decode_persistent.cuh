@@ -131,6 +131,33 @@ __device__ __forceinline__ size_t pk_a_index(int r, int k) {
     return ((size_t)((s * 4 + p) * 32 + g * 4 + t)) * 2 + hi;
 }
 
+// Code-generation knobs (A/B-measured, profiles/r2_codegen_ab.md): the kernel is one 12 K-instruction function under a 128-register
+// cap, and ptxas' allocation for the layer loop shifts with unrelated code (a smaller sampler made the LAYERS 4 % slower).  Out-of-line
+// phases get their own register allocation and keep the loop's code independent of the rest.
+#ifndef PK_ROPE_PRE           // qkv epilogue: RoPE table entry + column decomposition fetched before the packet wait
+#define PK_ROPE_PRE 1
+#endif
+#ifndef PK_OUTLINE            // bit 0: sampler, bit 1: attention phase, bit 2: GEMM phase
+#define PK_OUTLINE 0
+#endif
+#if PK_OUTLINE & 1
+#define PK_SMP_INLINE __noinline__
+#else
+#define PK_SMP_INLINE __forceinline__
+#endif
+#if PK_OUTLINE & 2
+#define PK_ATTN_INLINE __noinline__
+#else
+#define PK_ATTN_INLINE __forceinline__
+#endif
+#if PK_OUTLINE & 4
+#define PK_GEMM_INLINE __noinline__
+#else
+#define PK_GEMM_INLINE __forceinline__
+#endif
+
+extern __shared__ __align__(128) unsigned char pk_smem_raw[];
+
 struct PkSmem {
     unsigned char* ring;     // [PK_NSLOT][PK_SLOT_BYTES]
     float* red;              // [PK_WARPS][PK_NBMAX][PK_RED]   (attention scratch aliases it)
@@ -145,6 +172,23 @@ struct PkSmem {
     bf16* nw;                // [<= 1536] the phase's RMSNorm weights, staged by cp.async while the CTA waits for its A packets
 };
 static_assert(sizeof(PkAttnPlan) <= 1024 && PKP_WARPS == PK_WARPS && PKP_MAXSEG == PK_MAXSEG, "plan layout");
+__device__ __forceinline__ PkSmem pk_smem_layout() {
+    PkSmem sm;
+    unsigned char* q = pk_smem_raw;
+    sm.ring = q; q += PK_SMEM_RING;
+    sm.red = reinterpret_cast<float*>(q); q += PK_SMEM_RED;
+    sm.ssq = reinterpret_cast<float*>(q); q += 16 * 16 * 4;
+    sm.full = reinterpret_cast<uint64_t*>(q); q += 128;
+    sm.st = reinterpret_cast<PkStream*>(q); q += 128;
+    sm.own = reinterpret_cast<uint2*>(q); q += 2 * 32 * 8;
+    sm.qrow = reinterpret_cast<uint32_t*>(q); q += 3 * 6 * 128;
+    sm.plan = reinterpret_cast<PkAttnPlan*>(q); q += 1024;
+    sm.kvp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
+    sm.nwp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
+    sm.nw = reinterpret_cast<bf16*>(q);
+    return sm;
+}
+
 
 // ---------------------------------------------------------------------------------------------------------
 // weight stream: the producer thread walks the CTA's units in consumption order
@@ -291,9 +335,10 @@ __device__ __forceinline__ const bf16* pk_ctrl_next(const PkParams& P, int l) {
     return (P.has_ctrl && (l + 1) < P.L && (l + 1) % step3 == 0) ? P.ctrl[(l + 1) / step3] : nullptr;
 }
 
-__device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& sm, const int kind, const int l, const int pos,
-                                              const unsigned int tag, int blk_lo, int blk_hi, unsigned int& cons, long long* dbg, long long* wdbg_base,
-                                              float* trace_rows = nullptr) {
+__device__ PK_GEMM_INLINE unsigned int pk_gemm_phase(const PkParams& P, const int kind, const int l, const int pos,
+                                                      const unsigned int tag, int blk_lo, int blk_hi, unsigned int cons, long long* dbg, long long* wdbg_base,
+                                                      float* trace_rows = nullptr) {
+    const PkSmem sm = pk_smem_layout();
     const int par = l & 1;
     const bool NORM = (kind == 0 || kind == 2 || kind == 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -307,7 +352,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
 #else
     constexpr bool stamp = false;
 #endif
-    if (blk_lo >= blk_hi) return;                      // this CTA owns no columns of this phase
+    if (blk_lo >= blk_hi) return cons;                 // this CTA owns no columns of this phase
     if (stamp) dbg[0] = pk_now();
     long long* const wdbg = (wdbg_base != nullptr && lane == 0) ? wdbg_base + warp * 16 : nullptr;   // per-warp stamps (dev)
 #ifdef PK_TRACE
@@ -343,7 +388,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
     // table load (an L2 round trip) are taken off the path between the reduction and the packet stores
     int q_col = 0;                                         // sec << 16 | head << 6 | el (one register across the poll and the MMA)
     float2 q_cs = make_float2(1.f, 0.f);
-    if (kind == 0 && er == 0 && blk_lo + ej < blk_hi) {
+    if (PK_ROPE_PRE && kind == 0 && er == 0 && blk_lo + ej < blk_hi) {
         const int n = (blk_lo + ej) * 8 + 2 * ecp;
         const int sec = n / P.dim, w = n - sec * P.dim;
         q_col = (sec << 16) | w;
@@ -538,7 +583,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
                 if (kind == 0) {
                     int sec = q_col >> 16, head = (q_col & 0xffff) >> 6, el = q_col & 63;
                     float2 cs2 = q_cs;
-                    if (bb != blk_lo) {   // later batches (only models with more than 4 qkv blocks per CTA): recompute
+                    if (!PK_ROPE_PRE || bb != blk_lo) {   // later batches (only models with more than 4 qkv blocks per CTA): recompute
                         const int n = (bb + ej) * 8 + 2 * ecp;
                         sec = n / P.dim;
                         const int w = n - sec * P.dim;
@@ -602,6 +647,7 @@ __device__ __forceinline__ void pk_gemm_phase(const PkParams& P, const PkSmem& s
         b0 += nb;
         first = false;
     }
+    return cons;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -654,7 +700,8 @@ __device__ __forceinline__ void pk_attn_finalize(const PkParams& P, float Mx, fl
 // ("parts").  Within a part the four 8-lane row slots of the warp take rows k0 + sub + 4 i, the loads of two blocks of 4 rows
 // per slot in flight at once; the slots are merged with shuffles and the warp leaves one partial per part in shared memory:
 // entry (warp, part) = {-, m, l, -, acc[64]}.
-__device__ __forceinline__ void pk_attn_phase(const PkParams& P, const PkSmem& sm, int layer, int pos, unsigned int tag, int par, long long* dbg) {
+__device__ PK_ATTN_INLINE void pk_attn_phase(const PkParams& P, int layer, int pos, unsigned int tag, int par, long long* dbg) {
+    const PkSmem sm = pk_smem_layout();
     constexpr int EPL = 8, UNR = 4, ENT = 68;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane >> 3, cl = lane & 7;
     const PkAttnPlan& pl = *sm.plan;
@@ -841,25 +888,15 @@ __device__ __forceinline__ void pk_write_embedding(const PkParams& P, uint2* h2,
     }
 }
 
+__device__ PK_SMP_INLINE void pk_sample(const SampleArgs& a, int b) {
+    static_assert(SMP_SCRATCH <= PK_SMEM_RED, "the sampler's scratch aliases the reduction buffer");
+    sample_body<PK_THREADS>(a, b, pk_smem_raw + PK_SMEM_RING);
+}
+
 __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_constant__ PkParams P) {
-    extern __shared__ __align__(128) unsigned char pk_smem_raw[];
     __shared__ int s_tok;
     __shared__ int s_lo[5], s_hi[5];                       // this CTA's block ranges per GEMM kind
-    PkSmem sm;
-    {
-        unsigned char* q = pk_smem_raw;
-        sm.ring = q; q += PK_SMEM_RING;
-        sm.red = reinterpret_cast<float*>(q); q += PK_SMEM_RED;
-        sm.ssq = reinterpret_cast<float*>(q); q += 16 * 16 * 4;
-        sm.full = reinterpret_cast<uint64_t*>(q); q += 128;
-        sm.st = reinterpret_cast<PkStream*>(q); q += 128;
-        sm.own = reinterpret_cast<uint2*>(q); q += 2 * 32 * 8;
-        sm.qrow = reinterpret_cast<uint32_t*>(q); q += 3 * 6 * 128;
-        sm.plan = reinterpret_cast<PkAttnPlan*>(q); q += 1024;
-        sm.kvp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
-        sm.nwp = reinterpret_cast<const bf16**>(q); q += 2 * PK_MAXL * 8;
-        sm.nw = reinterpret_cast<bf16*>(q);
-    }
+    const PkSmem sm = pk_smem_layout();
     const int tid = threadIdx.x;
     const int G = gridDim.x;
     if (tid == 0) {
@@ -919,8 +956,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
             a.pos_ptr = nullptr; a.done_ctr = nullptr; a.pos_val = pos; a.step = step; a.ssq_rows = nullptr;
             a.h_out = nullptr; a.tok_buf = nullptr;
             a.dbg_ts = (dbg_step && blockIdx.x == 0) ? dbg_cta + 48 : nullptr;   // (slots 8 .. 47: the five phases of layer 3)
-            static_assert(SMP_SCRATCH <= PK_SMEM_RED, "the sampler's scratch aliases the reduction buffer");
-            sample_body<PK_THREADS>(a, blockIdx.x, reinterpret_cast<unsigned char*>(sm.red));
+            pk_sample(a, blockIdx.x);
             __syncthreads();
             if (tid == 0) s_tok = P.forced != nullptr ? __ldg(P.forced + (size_t)blockIdx.x * P.forced_ld + step)
                                                       : ld_cg(a.idx_out + (size_t)blockIdx.x * a.tokens_ld + step);
@@ -946,9 +982,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pk_decode_kernel(const __grid_c
             const int nph = l < P.L ? 5 : 1;
             for (int ph = 0; ph < nph; ++ph) {
                 long long* dbg = (dbg_step && l == 3) ? dbg_cta + 8 + 8 * ph : (dbg_step && l == P.L) ? dbg_cta + 56 : nullptr;   // (head: slots 56 .. 60)
-                if (l < P.L && ph == 1) { pk_attn_phase(P, sm, l, p, tag, par, dbg); continue; }
+                if (l < P.L && ph == 1) { pk_attn_phase(P, l, p, tag, par, dbg); continue; }
                 const int kind = l == P.L ? 4 : (ph == 0 ? 0 : ph - 1);
-                pk_gemm_phase(P, sm, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg,
+                cons = pk_gemm_phase(P, kind, l, p, tag, s_lo[kind], s_hi[kind], cons, dbg,
                               (dbg != nullptr && (int)blockIdx.x == 77 % (int)gridDim.x) ? P.dbg + (size_t)gridDim.x * 64 + (size_t)ph * 256 : nullptr,
                               (kind == 4 && P.trace != nullptr) ? P.trace + (size_t)(step + 1) * P.b_eff * P.V : nullptr);
             }

@@ -17,7 +17,7 @@ m.adapter_mlp.forward = lambda x: x
 cond = torch.randn(B, 120, 2048, device="cuda", dtype=torch.bfloat16)
 masks = torch.ones(B, 120, dtype=torch.int64, device="cuda")
 ctrl = torch.randn(B, N, 1280, device="cuda", dtype=torch.bfloat16) * 0.1
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", 3))):
     torch.cuda.synchronize(); t0 = time.time()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
