@@ -134,11 +134,11 @@ __device__ __forceinline__ size_t pk_a_index(int r, int k) {
 // Code-generation knobs (A/B-measured, profiles/r2_codegen_ab.md): the kernel is one 12 K-instruction function under a 128-register
 // cap, and ptxas' allocation for the layer loop shifts with unrelated code (a smaller sampler made the LAYERS 4 % slower).  Out-of-line
 // phases get their own register allocation and keep the loop's code independent of the rest.
-#ifndef PK_ROPE_PRE           // qkv epilogue: RoPE table entry + column decomposition fetched before the packet wait
-#define PK_ROPE_PRE 1
+#ifndef PK_ROPE_PRE           // qkv epilogue: RoPE table entry + column decomposition fetched before the packet wait (measured slower: off)
+#define PK_ROPE_PRE 0
 #endif
-#ifndef PK_OUTLINE            // bit 0: sampler, bit 1: attention phase, bit 2: GEMM phase
-#define PK_OUTLINE 0
+#ifndef PK_OUTLINE            // bit 0: sampler, bit 1: attention phase, bit 2: GEMM phase (1 = the A/B winner)
+#define PK_OUTLINE 1
 #endif
 #if PK_OUTLINE & 1
 #define PK_SMP_INLINE __noinline__
