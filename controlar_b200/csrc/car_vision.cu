@@ -249,8 +249,8 @@ extern "C" int car_dino_forward(CarDino* m, const void* image, int32_t B, int32_
 // =========================================================================================================
 // VQGAN tokenizer
 // =========================================================================================================
-struct ConvW { bf16* w; bf16* b; int cin, cin_pad, cout, k; };
-struct NormW { bf16 *w, *b; int c; };
+struct ConvW { bf16* w; bf16* b; int cin, cin_pad, cout, k; bf16* w3; float* bf; };     // w3 / bf: split-bf16 weights + fp32 bias (encoder)
+struct NormW { bf16 *w, *b; int c; float *wf, *bff; };                                   // wf / bff: fp32 copies (encoder)
 struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin; };
 struct AttnW { NormW n; ConvW q, k, v, o; };
 
@@ -271,9 +271,22 @@ struct CarVQ {
 
 struct TensorCursor { const void* const* t; int n; int i; };
 
-static int take_conv(CarVQ* m, cudaStream_t st, TensorCursor& tc, int cout, int cin, int k, ConvW* c) {
+static int keep_f32(CarVQ* m, cudaStream_t st, const void* src, long long n, float** dst) {
+    CAR_CUDA(cudaMalloc((void**)dst, (size_t)n * 4));
+    m->owned.push_back(*dst);
+    CAR_CUDA(cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    return CAR_OK;
+}
+static int take_conv(CarVQ* m, cudaStream_t st, TensorCursor& tc, int cout, int cin, int k, ConvW* c, bool x3 = false) {
     if (tc.i + 2 > tc.n) CAR_FAIL(CAR_ERR_ARG, "tensor list too short");
-    c->cin = cin; c->cout = cout; c->k = k; c->cin_pad = (cin + 31) & ~31;
+    c->cin = cin; c->cout = cout; c->k = k; c->cin_pad = (cin + 31) & ~31; c->w3 = nullptr; c->bf = nullptr;
+    if (x3) {   // fp32-grade encoder path (vision.cuh "x3"): [w_hi | w_hi | w_lo] per tap + the fp32 bias
+        const long long n3 = (long long)cout * k * k * c->cin_pad;
+        CAR_CUDA(cudaMalloc((void**)&c->w3, (size_t)n3 * 3 * 2));
+        m->owned.push_back(c->w3);
+        CAR_LAUNCH(conv_weight_pack_x3_kernel, gsz(n3), 256, 0, st, (const float*)tc.t[tc.i], c->w3, cout, cin, k, k, c->cin_pad);
+        CAR_TRY(keep_f32(m, st, tc.t[tc.i + 1], cout, &c->bf));
+    }
     const long long n = (long long)cout * k * k * c->cin_pad;
     CAR_CUDA(cudaMalloc((void**)&c->w, (size_t)n * 2));
     m->owned.push_back(c->w);
@@ -282,26 +295,27 @@ static int take_conv(CarVQ* m, cudaStream_t st, TensorCursor& tc, int cout, int 
     tc.i += 2;
     return CAR_OK;
 }
-static int take_norm(CarVQ* m, cudaStream_t st, TensorCursor& tc, int c, NormW* nw) {
+static int take_norm(CarVQ* m, cudaStream_t st, TensorCursor& tc, int c, NormW* nw, bool x3 = false) {
     if (tc.i + 2 > tc.n) CAR_FAIL(CAR_ERR_ARG, "tensor list too short");
-    nw->c = c;
+    nw->c = c; nw->wf = nullptr; nw->bff = nullptr;
+    if (x3) { CAR_TRY(keep_f32(m, st, tc.t[tc.i], c, &nw->wf)); CAR_TRY(keep_f32(m, st, tc.t[tc.i + 1], c, &nw->bff)); }
     CAR_TRY(to_bf16<float>(st, m->owned, tc.t[tc.i], c, &nw->w));
     CAR_TRY(to_bf16<float>(st, m->owned, tc.t[tc.i + 1], c, &nw->b));
     tc.i += 2;
     return CAR_OK;
 }
 // canonical order inside a ResnetBlock: norm1.{w,b} conv1.{w,b} norm2.{w,b} conv2.{w,b} [nin_shortcut.{w,b}]
-static int take_res(CarVQ* m, cudaStream_t st, TensorCursor& tc, int cin, int cout, ResW* r) {
-    CAR_TRY(take_norm(m, st, tc, cin, &r->n1)); CAR_TRY(take_conv(m, st, tc, cout, cin, 3, &r->c1));
-    CAR_TRY(take_norm(m, st, tc, cout, &r->n2)); CAR_TRY(take_conv(m, st, tc, cout, cout, 3, &r->c2));
+static int take_res(CarVQ* m, cudaStream_t st, TensorCursor& tc, int cin, int cout, ResW* r, bool x3 = false) {
+    CAR_TRY(take_norm(m, st, tc, cin, &r->n1, x3)); CAR_TRY(take_conv(m, st, tc, cout, cin, 3, &r->c1, x3));
+    CAR_TRY(take_norm(m, st, tc, cout, &r->n2, x3)); CAR_TRY(take_conv(m, st, tc, cout, cout, 3, &r->c2, x3));
     r->has_nin = cin != cout;
-    if (r->has_nin) CAR_TRY(take_conv(m, st, tc, cout, cin, 1, &r->nin));
+    if (r->has_nin) CAR_TRY(take_conv(m, st, tc, cout, cin, 1, &r->nin, x3));
     return CAR_OK;
 }
 // AttnBlock: norm.{w,b} q.{w,b} k.{w,b} v.{w,b} proj_out.{w,b}
-static int take_attn(CarVQ* m, cudaStream_t st, TensorCursor& tc, int c, AttnW* a) {
-    CAR_TRY(take_norm(m, st, tc, c, &a->n)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->q)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->k));
-    CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->v)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->o));
+static int take_attn(CarVQ* m, cudaStream_t st, TensorCursor& tc, int c, AttnW* a, bool x3 = false) {
+    CAR_TRY(take_norm(m, st, tc, c, &a->n, x3)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->q, x3)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->k, x3));
+    CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->v, x3)); CAR_TRY(take_conv(m, st, tc, c, c, 1, &a->o, x3));
     return CAR_OK;
 }
 
@@ -310,22 +324,22 @@ static int vq_build(CarVQ* m, const void* const* tensors, int n, cudaStream_t st
     TensorCursor tc{tensors, n, 0};
     const int ch = d.ch, nres = d.n_levels, nrb = d.num_res_blocks;
     // ---- encoder (vq_model.py:65-125)
-    CAR_TRY(take_conv(m, st, tc, ch, 3, 3, &m->e_conv_in));
+    CAR_TRY(take_conv(m, st, tc, ch, 3, 3, &m->e_conv_in, true));
     m->e_res.resize(nres); m->e_attn.resize(nres); m->e_down.resize(nres); m->e_has_down.assign(nres, false);
     int block_in = ch;
     for (int lvl = 0; lvl < nres; ++lvl) {
         block_in = ch * (lvl == 0 ? 1 : d.ch_mult[lvl - 1]);
         const int block_out = ch * d.ch_mult[lvl];
         for (int b = 0; b < nrb; ++b) {
-            ResW r; CAR_TRY(take_res(m, st, tc, block_in, block_out, &r)); m->e_res[lvl].push_back(r);
+            ResW r; CAR_TRY(take_res(m, st, tc, block_in, block_out, &r, true)); m->e_res[lvl].push_back(r);
             block_in = block_out;
-            if (lvl == nres - 1) { AttnW a; CAR_TRY(take_attn(m, st, tc, block_in, &a)); m->e_attn[lvl].push_back(a); }
+            if (lvl == nres - 1) { AttnW a; CAR_TRY(take_attn(m, st, tc, block_in, &a, true)); m->e_attn[lvl].push_back(a); }
         }
-        if (lvl != nres - 1) { CAR_TRY(take_conv(m, st, tc, block_in, block_in, 3, &m->e_down[lvl])); m->e_has_down[lvl] = true; }
+        if (lvl != nres - 1) { CAR_TRY(take_conv(m, st, tc, block_in, block_in, 3, &m->e_down[lvl], true)); m->e_has_down[lvl] = true; }
     }
-    CAR_TRY(take_res(m, st, tc, block_in, block_in, &m->e_mid0)); CAR_TRY(take_attn(m, st, tc, block_in, &m->e_mid1));
-    CAR_TRY(take_res(m, st, tc, block_in, block_in, &m->e_mid2));
-    CAR_TRY(take_norm(m, st, tc, block_in, &m->e_norm_out)); CAR_TRY(take_conv(m, st, tc, d.z_channels, block_in, 3, &m->e_conv_out));
+    CAR_TRY(take_res(m, st, tc, block_in, block_in, &m->e_mid0, true)); CAR_TRY(take_attn(m, st, tc, block_in, &m->e_mid1, true));
+    CAR_TRY(take_res(m, st, tc, block_in, block_in, &m->e_mid2, true));
+    CAR_TRY(take_norm(m, st, tc, block_in, &m->e_norm_out, true)); CAR_TRY(take_conv(m, st, tc, d.z_channels, block_in, 3, &m->e_conv_out, true));
     // ---- decoder (vq_model.py:129-195)
     block_in = ch * d.ch_mult[nres - 1];
     CAR_TRY(take_conv(m, st, tc, block_in, d.z_channels, 3, &m->d_conv_in));
@@ -349,7 +363,7 @@ static int vq_build(CarVQ* m, const void* const* tensors, int n, cudaStream_t st
     m->owned.push_back(m->codebook_n);
     CAR_LAUNCH(codebook_normalize_kernel, (d.codebook_size + 255) / 256, 256, 0, st, (const float*)tc.t[tc.i], m->codebook_n, d.codebook_size, d.embed_dim);
     tc.i += 1;
-    CAR_TRY(take_conv(m, st, tc, d.embed_dim, d.z_channels, 1, &m->quant_conv));
+    CAR_TRY(take_conv(m, st, tc, d.embed_dim, d.z_channels, 1, &m->quant_conv, true));
     CAR_TRY(take_conv(m, st, tc, d.z_channels, d.embed_dim, 1, &m->post_quant));
     if (tc.i != tc.n) CAR_FAIL(CAR_ERR_ARG, "tensor list length does not match the VQ architecture");
     return CAR_OK;
@@ -511,6 +525,80 @@ extern "C" int car_vq_decode(CarVQ* m, const float* quant, int32_t B, int32_t h,
     return vq_decode_impl(m, nullptr, quant, B, h, w, out, stream);
 }
 
+// ---- VQModel.encode (vq_model.py:41-46) at fp32 grade: the "x3" split-bf16 path of vision.cuh ----
+// fp32 NHWC activations; every convolution = one launch of the bf16 implicit-GEMM kernel over tripled K, fp32 output / bias / residual.
+struct ActF { float* p; int B, H, W, C; long long npix() const { return (long long)B * H * W; } long long n() const { return npix() * C; } };
+struct EncScratch { bf16 *t3, *x3; float *h1, *sc; float* stats; float *qf, *kf, *vf, *S, *P, *ctx; bf16 *q3, *k3, *P3, *vT3; };
+
+static int split3(cudaStream_t st, const float* x, bf16* y, long long npix, int C, int bside = 0) {
+    CAR_LAUNCH(split3_kernel, gsz(npix * C), 256, 0, st, x, y, npix, C, bside);
+    return CAR_OK;
+}
+// a3: S3 activations [B][Hs][Ws][3 cin_pad]; out fp32 [B][Ho][Wo][cout] (+ fp32 residual of the same shape)
+static int conv_x3(cudaStream_t st, const ConvW& c, const bf16* a3, int B, int Hs, int Ws, int stride2, float* out, const float* resid, int Ho, int Wo) {
+    if (!c.w3 || !c.bf) CAR_FAIL(CAR_ERR_STATE, "convolution has no split-bf16 weights (encoder layers only)");
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = a3; p.B = c.w3; p.M = B * Ho * Wo; p.N = c.cout; p.K = c.k * c.k * 3 * c.cin_pad; p.ldb = p.K; p.alpha = 1.f;
+    if (c.k == 1) { p.amode = A_PLAIN; p.lda = 3 * c.cin_pad; }
+    else { p.amode = stride2 ? A_CONV3x3S2 : A_CONV3x3; p.Hs = Hs; p.Ws = Ws; p.Cin = 3 * c.cin_pad; p.ups = 0; }
+    p.Ho = Ho; p.Wo = Wo;
+    p.bias_f = c.bf; p.C = out; p.ldc = c.cout; p.out_mode = 1; p.resid_f = resid; p.ldr = c.cout;
+    return dense(st, p);
+}
+static int gn_x3(cudaStream_t st, const NormW& nw, const ActF& x, bf16* y3, int swish, float* stats) {
+    const int G = 32;
+    CAR_LAUNCH(groupnorm_stats_f32_kernel, x.B * G, 512, 0, st, (const float*)x.p, stats, x.H * x.W, x.C, G);
+    CAR_LAUNCH(groupnorm_apply_split3_kernel, gsz(x.n()), 256, 0, st, (const float*)x.p, (const float*)stats, (const float*)nw.wf, (const float*)nw.bff, y3,
+               x.n(), x.H * x.W, x.C, G, swish);
+    return CAR_OK;
+}
+// ResnetBlock.forward (vq_model.py:300-315)
+static int res_x3(cudaStream_t st, const ResW& r, ActF& x, float* out, EncScratch& s) {
+    CAR_TRY(gn_x3(st, r.n1, x, s.t3, 1, s.stats));
+    CAR_TRY(conv_x3(st, r.c1, s.t3, x.B, x.H, x.W, 0, s.h1, nullptr, x.H, x.W));
+    ActF h{s.h1, x.B, x.H, x.W, r.c1.cout};
+    CAR_TRY(gn_x3(st, r.n2, h, s.t3, 1, s.stats));
+    const float* sc = x.p;
+    if (r.has_nin) {
+        CAR_TRY(split3(st, x.p, s.x3, x.npix(), x.C));
+        CAR_TRY(conv_x3(st, r.nin, s.x3, x.B, x.H, x.W, 0, s.sc, nullptr, x.H, x.W));
+        sc = s.sc;
+    }
+    CAR_TRY(conv_x3(st, r.c2, s.t3, x.B, x.H, x.W, 0, out, sc, x.H, x.W));
+    x.p = out; x.C = r.c2.cout;
+    return CAR_OK;
+}
+// AttnBlock.forward (vq_model.py:328-352): single head over H*W tokens, scale C^-0.5, everything fp32-grade
+static int attn_x3(cudaStream_t st, const AttnW& a, ActF& x, float* out, EncScratch& s) {
+    const int C = x.C, hw = x.H * x.W, B = x.B;
+    const int hwp = (hw + 31) & ~31;
+    const long long rows = (long long)B * hw;
+    CAR_TRY(gn_x3(st, a.n, x, s.t3, 0, s.stats));
+    CAR_TRY(conv_x3(st, a.q, s.t3, B, x.H, x.W, 0, s.qf, nullptr, x.H, x.W));
+    CAR_TRY(conv_x3(st, a.k, s.t3, B, x.H, x.W, 0, s.kf, nullptr, x.H, x.W));
+    CAR_TRY(conv_x3(st, a.v, s.t3, B, x.H, x.W, 0, s.vf, nullptr, x.H, x.W));
+    CAR_TRY(split3(st, s.qf, s.q3, rows, C, 0));
+    CAR_TRY(split3(st, s.kf, s.k3, rows, C, 1));
+    {   // scores [B][hw][hwp] fp32
+        DenseP p = dp_plain(s.q3, 3 * C, s.k3, 3 * C, hw, hw, 3 * C, s.S, hwp);
+        p.sA = (long long)hw * 3 * C; p.sB = (long long)hw * 3 * C; p.sC = (long long)hw * hwp; p.alpha = 1.0f / sqrtf((float)C); p.out_mode = 1;
+        CAR_TRY(dense(st, p, B));
+    }
+    CAR_LAUNCH(softmax_rows_f32_kernel, (unsigned)rows, 256, 0, st, (const float*)s.S, s.P, hw, hwp);
+    CAR_TRY(split3(st, s.P, s.P3, rows, hwp, 0));
+    CAR_LAUNCH(transpose_split3b_kernel, gsz((long long)B * C * hwp), 256, 0, st, (const float*)s.vf, s.vT3, B, hw, hwp, C);
+    {   // context [B][hw][C] fp32
+        DenseP p = dp_plain(s.P3, 3 * hwp, s.vT3, 3 * hwp, hw, C, 3 * hwp, s.ctx, C);
+        p.sA = (long long)hw * 3 * hwp; p.sB = (long long)C * 3 * hwp; p.sC = (long long)hw * C; p.out_mode = 1;
+        CAR_TRY(dense(st, p, B));
+    }
+    CAR_TRY(split3(st, s.ctx, s.q3, rows, C, 0));              // (q3 is free again)
+    CAR_TRY(conv_x3(st, a.o, s.q3, B, x.H, x.W, 0, out, x.p, x.H, x.W));
+    x.p = out;
+    return CAR_OK;
+}
+
 // VQModel.encode (vq_model.py:41-46): image fp32 NCHW [B][3][H][W] -> indices int32 [B*h*w] (+ quant fp32 [B][e][h][w])
 extern "C" int car_vq_encode(CarVQ* m, const float* img, int32_t B, int32_t H, int32_t W, int32_t* idx_out, float* quant_out,
                              void* stream) {
@@ -520,40 +608,53 @@ extern "C" int car_vq_encode(CarVQ* m, const float* img, int32_t B, int32_t H, i
     const int down = 1 << (d.n_levels - 1);
     if (H % down || W % down) CAR_FAIL(CAR_ERR_ARG, "image size must be a multiple of the down-sampling factor");
     const int h = H / down, w = W / down;
-    VqScratch s; bf16 *bA, *bB; void* extra;
     const size_t npix = (size_t)B * h * w;
-    CAR_TRY(vq_scratch(st, m, B, H, W, h, w, d.ch, s, &bA, &bB, (size_t)B * H * W * 32 * 2 + npix * 8 * 4 * 2 + 1024, &extra));
-    bf16* x0 = (bf16*)extra;
-    float* zf = (float*)((char*)extra + (((size_t)B * H * W * 32 * 2 + 255) & ~(size_t)255));
-    float* zq = zf + npix * 8;
-    CAR_LAUNCH((nchw_to_nhwc_bf16_kernel<float>), gsz((long long)B * H * W * 32), 256, 0, st, img, x0, B, 3, H * W, 32);
-    Act x{x0, B, H, W, 32};
-    auto flip = [&](bf16* used) { return used == bA ? bB : bA; };
-    CAR_TRY(conv_fwd(st, m->e_conv_in, x, 0, 0, bA, nullptr, H, W));
-    x = Act{bA, B, H, W, m->e_conv_in.cout};
+    const int hw = h * w, hwp = (hw + 31) & ~31, Cmax = d.ch * d.ch_mult[d.n_levels - 1];
+    // workspace: fp32 activations (largest: ch channels at full resolution) and their S3 forms
+    const size_t actf = (size_t)B * H * W * d.ch * 4, act3 = (size_t)B * H * W * d.ch * 3 * 2;
+    const size_t x0 = (size_t)B * H * W * 32 * 3 * 2;
+    const size_t af = npix * Cmax * 4, a3 = npix * Cmax * 3 * 2;
+    const size_t need = 4 * (actf + 256) + 2 * (act3 + 256) + x0 + 256 + (size_t)B * 32 * 2 * 4 + 256 + 4 * (af + 256) + 2 * (a3 + 256) +
+                        2 * ((size_t)B * hw * hwp * 4 + 256) + (size_t)B * hw * hwp * 3 * 2 + 256 + (size_t)B * Cmax * hwp * 3 * 2 + 256 + npix * 8 * 4 * 2 + 1024;
+    CAR_TRY(m->ws.reserve(need));
+    m->ws.reset();
+    float* fA = (float*)m->ws.take(actf); float* fB = (float*)m->ws.take(actf);
+    EncScratch s;
+    s.h1 = (float*)m->ws.take(actf); s.sc = (float*)m->ws.take(actf);
+    s.t3 = (bf16*)m->ws.take(act3); s.x3 = (bf16*)m->ws.take(act3);
+    bf16* img3 = (bf16*)m->ws.take(x0);
+    s.stats = (float*)m->ws.take((size_t)B * 32 * 2 * 4);
+    s.qf = (float*)m->ws.take(af); s.kf = (float*)m->ws.take(af); s.vf = (float*)m->ws.take(af); s.ctx = (float*)m->ws.take(af);
+    s.q3 = (bf16*)m->ws.take(a3); s.k3 = (bf16*)m->ws.take(a3);
+    s.S = (float*)m->ws.take((size_t)B * hw * hwp * 4); s.P = (float*)m->ws.take((size_t)B * hw * hwp * 4);
+    s.P3 = (bf16*)m->ws.take((size_t)B * hw * hwp * 3 * 2); s.vT3 = (bf16*)m->ws.take((size_t)B * Cmax * hwp * 3 * 2);
+    float* zf = (float*)m->ws.take(npix * 8 * 4); float* zq = (float*)m->ws.take(npix * 8 * 4);
+
+    CAR_LAUNCH(nchw_to_nhwc_split3_kernel, gsz((long long)B * H * W * 32), 256, 0, st, img, img3, B, 3, H * W, 32);
+    auto flip = [&](float* used) { return used == fA ? fB : fA; };
+    CAR_TRY(conv_x3(st, m->e_conv_in, img3, B, H, W, 0, fA, nullptr, H, W));
+    ActF x{fA, B, H, W, m->e_conv_in.cout};
     for (int lvl = 0; lvl < d.n_levels; ++lvl) {
         for (size_t b = 0; b < m->e_res[lvl].size(); ++b) {
-            CAR_TRY(res_fwd(st, m->e_res[lvl][b], x, flip(x.p), s));
-            if (!m->e_attn[lvl].empty()) CAR_TRY(attn_fwd(st, m->e_attn[lvl][b], x, flip(x.p), s));
+            CAR_TRY(res_x3(st, m->e_res[lvl][b], x, flip(x.p), s));
+            if (!m->e_attn[lvl].empty()) CAR_TRY(attn_x3(st, m->e_attn[lvl][b], x, flip(x.p), s));
         }
-        if (m->e_has_down[lvl]) {
-            bf16* o = flip(x.p);
-            CAR_TRY(conv_fwd(st, m->e_down[lvl], x, 0, 1, o, nullptr, x.H / 2, x.W / 2));
-            x = Act{o, B, x.H / 2, x.W / 2, m->e_down[lvl].cout};
+        if (m->e_has_down[lvl]) {   // Downsample (vq_model.py:382-397): pad (0,1,0,1), 3x3 stride 2
+            float* o = flip(x.p);
+            CAR_TRY(split3(st, x.p, s.x3, x.npix(), x.C));
+            CAR_TRY(conv_x3(st, m->e_down[lvl], s.x3, B, x.H, x.W, 1, o, nullptr, x.H / 2, x.W / 2));
+            x = ActF{o, B, x.H / 2, x.W / 2, m->e_down[lvl].cout};
         }
     }
-    CAR_TRY(res_fwd(st, m->e_mid0, x, flip(x.p), s));
-    CAR_TRY(attn_fwd(st, m->e_mid1, x, flip(x.p), s));
-    CAR_TRY(res_fwd(st, m->e_mid2, x, flip(x.p), s));
-    CAR_TRY(gn_fwd(st, m->e_norm_out, x, s.t0, 1, s.stats));
-    Act y{s.t0, B, x.H, x.W, x.C};
-    bf16* zc = flip(x.p);
-    CAR_TRY(conv_fwd(st, m->e_conv_out, y, 0, 0, zc, nullptr, x.H, x.W));
-    Act z{zc, B, x.H, x.W, d.z_channels};
-    bf16* z8 = flip(zc);
-    CAR_TRY(conv_fwd(st, m->quant_conv, z, 0, 0, z8, nullptr, x.H, x.W));     // [npix][embed_dim]
-    CAR_LAUNCH(take_channels_f32_kernel, gsz((long long)npix * d.embed_dim), 256, 0, st, z8, zf, (long long)npix, d.embed_dim, d.embed_dim);
-    CAR_LAUNCH(vq_argmin_kernel, (unsigned)((npix + 127) / 128), 128, 0, st, zf, m->codebook_n, idx_out, quant_out ? zq : nullptr, (long long)npix, d.embed_dim, d.codebook_size);
+    CAR_TRY(res_x3(st, m->e_mid0, x, flip(x.p), s));
+    CAR_TRY(attn_x3(st, m->e_mid1, x, flip(x.p), s));
+    CAR_TRY(res_x3(st, m->e_mid2, x, flip(x.p), s));
+    CAR_TRY(gn_x3(st, m->e_norm_out, x, s.t3, 1, s.stats));
+    float* zc = flip(x.p);
+    CAR_TRY(conv_x3(st, m->e_conv_out, s.t3, B, x.H, x.W, 0, zc, nullptr, x.H, x.W));              // [npix][z_channels]
+    CAR_TRY(split3(st, zc, s.x3, (long long)npix, d.z_channels));
+    CAR_TRY(conv_x3(st, m->quant_conv, s.x3, B, x.H, x.W, 0, zf, nullptr, x.H, x.W));              // [npix][embed_dim] fp32
+    CAR_LAUNCH(vq_argmin_kernel, (unsigned)((npix + 127) / 128), 128, 0, st, (const float*)zf, m->codebook_n, idx_out, quant_out ? zq : nullptr, (long long)npix, d.embed_dim, d.codebook_size);
     if (quant_out) CAR_LAUNCH(nhwc_to_nchw_f32_kernel, gsz((long long)npix * d.embed_dim), 256, 0, st, zq, quant_out, B, h * w, d.embed_dim);
     return CAR_OK;
 }

@@ -28,6 +28,8 @@ struct DenseP {
     // epilogue: v = acc*alpha (+bias[n] | bias[m]); v = rnd(v); act; (*scale[n]); (+resid); store
     float alpha;
     const bf16* bias; int bias_along_m;
+    const float* bias_f;               // fp32 bias (per n), fp32-output modes
+    const float* resid_f;              // fp32 residual [M, ldr] (+ z * sR), fp32-output modes: added without rounding
     int act;
     const bf16* scale;                 // LayerScale lambda (per n), applied after rounding: r(r(v)*scale)
     const bf16* resid; int ldr;        // residual added last: r(v + resid)
@@ -176,6 +178,8 @@ static __global__ void __launch_bounds__(DG_THREADS) dense_gemm_kernel(DenseP p)
                     if (n >= p.N) continue;
                     float v = acc[i][j][hh * 2 + e] * p.alpha;
                     if (p.bias) v += tof(p.bias[p.bias_along_m ? m : n]);
+                    if (p.bias_f) v += p.bias_f[n];
+                    if (p.resid_f) v += p.resid_f[(size_t)z * p.sR + (size_t)m * p.ldr + n];
                     if (p.out_mode == 0) v = rnd<bf16>(v);
                     if (p.act == ACT_GELU_TANH) v = rnd<bf16>(gelu_tanh_f(v));
                     else if (p.act == ACT_GELU_ERF) v = rnd<bf16>(gelu_erf_f(v));

@@ -117,6 +117,119 @@ __global__ void cast_to_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__
         y[i] = fromf<bf16>(tof(x[i]));
 }
 
+// ---- fp32-grade path of the VQGAN encoder ("x3": split-bf16 operands, three partial products, fp32 accumulate) ----
+// VQModel.encode runs in fp32 in the reference (vq_model.py:41-46; sample / extract scripts keep the tokenizer in fp32) and its
+// arg-min indices must come out the same (index work is bit-exact), which a bf16 encoder cannot deliver: the
+// latent then carries ~1e-2 relative noise and 6-7 % of the indices flip.  Here every fp32 value x travels as the pair
+// hi = bf16(x), lo = bf16(x - hi) (x = hi + lo to 2^-17) and a product x·w is evaluated as hi·w_hi + lo·w_hi + hi·w_lo on the
+// tensor cores with fp32 accumulation, by tripling the GEMM's K dimension:
+//   activations "S3" : NHWC bf16 with 3C channels per pixel  [ hi(C) | lo(C) | hi(C) ]   (A side)
+//   weights     "W3" : [Cout][tap][3 Cin_pad]                [ w_hi  | w_hi  | w_lo  ]   (B side)
+// so the bf16 implicit-GEMM kernel (gemm_dense.cuh) is used unchanged, with fp32 output, fp32 bias and fp32 residual.
+__global__ void split3_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long npix, int C, int bside) {
+    const long long total = npix * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / C; const int c = (int)(i - pix * C);
+        const float v = x[i];
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* o = y + pix * 3 * C + c;
+        o[0] = hi; o[C] = bside ? hi : lo; o[2 * C] = bside ? lo : hi;       // A side: hi | lo | hi ; B side: hi | hi | lo
+    }
+}
+// image fp32 NCHW [B][C][HW] -> S3 NHWC with Cpad channels per part (zero padded)
+__global__ void nchw_to_nhwc_split3_kernel(const float* __restrict__ x, bf16* __restrict__ y, int B, int C, int HW, int Cpad) {
+    const long long total = (long long)B * HW * Cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const long long bp = i / Cpad;
+        const int pix = (int)(bp % HW), b = (int)(bp / HW);
+        const float v = c < C ? x[((size_t)b * C + c) * HW + pix] : 0.f;
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* o = y + bp * 3 * Cpad + c;
+        o[0] = hi; o[Cpad] = lo; o[2 * Cpad] = hi;
+    }
+}
+// conv weight fp32 [Cout][Cin][kh][kw] -> W3 bf16 [Cout][kh][kw][3 Cin_pad] = [ w_hi | w_hi | w_lo ] per tap
+__global__ void conv_weight_pack_x3_kernel(const float* __restrict__ w, bf16* __restrict__ y, int Cout, int Cin, int KH, int KW, int Cin_pad) {
+    const long long total = (long long)Cout * KH * KW * Cin_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin_pad);
+        long long r = i / Cin_pad;
+        const long long tapidx = r;                     // (o * KH + ky) * KW + kx
+        const int kx = (int)(r % KW); r /= KW;
+        const int ky = (int)(r % KH);
+        const int o = (int)(r / KH);
+        const float v = c < Cin ? w[(((size_t)o * Cin + c) * KH + ky) * KW + kx] : 0.f;
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* q = y + tapidx * 3 * Cin_pad + c;
+        q[0] = hi; q[Cin_pad] = hi; q[2 * Cin_pad] = lo;
+    }
+}
+// GroupNorm(32, eps 1e-6) statistics over NHWC fp32 (two-pass mean / variance in fp64-free fp32: mean first, then centred squares)
+__global__ void groupnorm_stats_f32_kernel(const float* __restrict__ x, float* __restrict__ stats /*[B*G][2]*/, int HW, int C, int G) {
+    __shared__ float red[32];
+    const int b = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+    const float* xb = x + (size_t)b * HW * C + g * cg;
+    const long long n = (long long)HW * cg;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += xb[(i / cg) * C + (i % cg)];
+    s = block_sum(s, red);
+    __shared__ float s_mean;
+    if (threadIdx.x == 0) s_mean = s / n;
+    __syncthreads();
+    const float mean = s_mean;
+    float ss = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float d = xb[(i / cg) * C + (i % cg)] - mean; ss += d * d; }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) { stats[blockIdx.x * 2] = mean; stats[blockIdx.x * 2 + 1] = rsqrtf(ss / n + 1e-6f); }
+}
+// y = GN(x) (*swish) in fp32, written as S3 (or plain fp32 when y3 is null)
+__global__ void groupnorm_apply_split3_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
+                                              const float* __restrict__ bsh, bf16* __restrict__ y3, long long total, int HW, int C, int G, int swish) {
+    const int cg = C / G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / C; const int c = (int)(i - pix * C);
+        const int b = (int)(pix / HW);
+        const float* st = stats + ((size_t)b * G + c / cg) * 2;
+        float v = (x[i] - st[0]) * st[1] * w[c] + bsh[c];
+        if (swish) v = v / (1.0f + expf(-v));
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* o = y3 + pix * 3 * C + c;
+        o[0] = hi; o[C] = lo; o[2 * C] = hi;
+    }
+}
+// soft-max over rows of fp32 scores, fp32 out (columns >= n of the padded row are zeroed)
+__global__ void softmax_rows_f32_kernel(const float* __restrict__ s, float* __restrict__ p, int n, int ld) {
+    __shared__ float red[32];
+    const float* sr = s + (size_t)blockIdx.x * ld;
+    float* pr = p + (size_t)blockIdx.x * ld;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(sr[i] - mx);
+    sum = block_sum(sum, red);
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) pr[i] = i < n ? expf(sr[i] - mx) / sum : 0.f;
+}
+// v fp32 [B][hw][C] -> V^T as a B-side split operand [B][C][3 hwp]  ( hi | hi | lo over the hw dimension, zero padded to hwp )
+__global__ void transpose_split3b_kernel(const float* __restrict__ v, bf16* __restrict__ y, int B, int hw, int hwp, int C) {
+    const long long total = (long long)B * C * hwp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % hwp);
+        const long long bc = i / hwp;
+        const int c = (int)(bc % C), b = (int)(bc / C);
+        const float x = t < hw ? v[((size_t)b * hw + t) * C + c] : 0.f;
+        const bf16 hi = __float2bfloat16_rn(x);
+        const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        bf16* o = y + bc * 3 * hwp + t;
+        o[0] = hi; o[hwp] = hi; o[2 * hwp] = lo;
+    }
+}
+
 // ---- control-map resize to multiples of the patch size P (dinov2_adapter.py:16-24) fused with the PxP patch im2col:
 // out[b*hw + py*w + px][c*P*P + ky*P + kx] (Kpad columns, zero padded) = resized[b][c][py*P+ky][px*P+kx]
 // mode 0: F.interpolate(mode='nearest')  src = floor(dst * in/out)

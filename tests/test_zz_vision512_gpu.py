@@ -87,11 +87,11 @@ def test_vq_encode_512_indices_vs_reference_golden():
     worst_gap = max(gaps) if gaps else 0.0
     _log(case="vq_encode_512", agree=agree, n_bad=len(gaps), worst_gap=worst_gap, median_ref_margin=float(margin.median()),
          frac_ref_margin_below_1e_3=float((margin < 1e-3).float().mean()))
-    # Measured on B200 (r2, gpurun_out/vision512.jsonl): 93.4 % of the 1024 indices equal the reference's, the worst mismatch picks a
-    # code 2.1e-2 further (squared distance on the unit sphere; the reference's own median best-vs-second margin is 2.2e-2).  The
-    # encoder runs bf16 tensor-core operands with bf16 activation storage where the reference is fp32, i.e. its latent carries ~1e-2
-    # relative noise: bit-exact indices need fp32-grade convolutions (open item).  The assertions pin the measured level.
-    tie = float(os.environ.get("CAR_VQ_TIE", "3e-2"))
+    # The encoder runs at fp32 grade (split-bf16 operands, three partial products, fp32 accumulate: csrc/vision.cuh "x3"), like the
+    # reference's fp32 VQModel.  (With the bf16 encoder of round 1: 93.4 % agreement, worst mismatch 2.1e-2 further than the reference's
+    # best code — the reference's own median best-vs-second margin is 2.2e-2.)  Bar: >= 99 % identical indices and every mismatch a
+    # near-tie of the reference's own distances (gap below 1e-3; 3 % of the positions have a reference margin below that).
+    tie = float(os.environ.get("CAR_VQ_TIE", "1e-3"))
     assert worst_gap < tie, f"a mismatching index is {worst_gap:.3e} worse than the reference's best in the reference's own distances"
-    assert agree > float(os.environ.get("CAR_VQ_AGREE", "0.90")), agree
+    assert agree > float(os.environ.get("CAR_VQ_AGREE", "0.99")), agree
     assert quant.shape == (1, 8, 32, 32)
