@@ -89,9 +89,10 @@ def test_vq_encode_512_indices_vs_reference_golden():
          frac_ref_margin_below_1e_3=float((margin < 1e-3).float().mean()))
     # The encoder runs at fp32 grade (split-bf16 operands, three partial products, fp32 accumulate: csrc/vision.cuh "x3"), like the
     # reference's fp32 VQModel.  (With the bf16 encoder of round 1: 93.4 % agreement, worst mismatch 2.1e-2 further than the reference's
-    # best code — the reference's own median best-vs-second margin is 2.2e-2.)  Bar: >= 99 % identical indices and every mismatch a
-    # near-tie of the reference's own distances (gap below 1e-3; 3 % of the positions have a reference margin below that).
-    tie = float(os.environ.get("CAR_VQ_TIE", "1e-3"))
+    # best code — the reference's own median best-vs-second margin is 2.2e-2.)  Measured on B200 with the fp32-grade path: 1024 of
+    # 1024 indices identical.  Bar: >= 99.9 % identical and every mismatch a near-tie of the reference's own distances (gap < 1e-4;
+    # 0.1 % of the positions have a reference margin below that).
+    tie = float(os.environ.get("CAR_VQ_TIE", "1e-4"))
     assert worst_gap < tie, f"a mismatching index is {worst_gap:.3e} worse than the reference's best in the reference's own distances"
-    assert agree > float(os.environ.get("CAR_VQ_AGREE", "0.99")), agree
+    assert agree >= float(os.environ.get("CAR_VQ_AGREE", "0.999")), agree
     assert quant.shape == (1, 8, 32, 32)
