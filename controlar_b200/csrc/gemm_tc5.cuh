@@ -29,8 +29,16 @@ struct Tc5P {
     int M, N, K;
     const bf16* resid; int ldr;
     bf16* C; int ldc;
-    int act;            // 0 none, 1 GELU-tanh
+    int act;            // 0 none, 1 GELU-tanh, 2 exact (erf) GELU
+    const bf16* bias;   // per output column, added to the fp32 accumulator before the bf16 rounding (nn.Linear / Conv2d bias)
+    const bf16* scale;  // per output column, applied after the activation: r(r(v) * scale) (DINOv2 LayerScale)
+    // 3x3 / pad 1 / stride 1 convolution over an NHWC tensor as an implicit GEMM (conv = 1): the A tile of output-pixel block
+    // (image n, rows 8 ty .., columns 16 tx ..) and k-block (tap, 64-channel block) is ONE 4-D TMA box {64 ch, 16 x, 8 y, 1 n} at
+    // (c0, 16 tx + kx - 1, 8 ty + ky - 1, n): out-of-bounds pixels (the padding) are zero-filled by TMA, and the box lands in shared
+    // memory as 128 rows x 128 bytes — exactly the K-major SWIZZLE_128B operand tile of the plain GEMM.
+    int conv, H, W, tiles_x, tiles_y, cblks;
 };
+constexpr int T5_TW = 16, T5_TH = 8;                                            // output-pixel block of a conv tile (T5_TW * T5_TH = T5_BM)
 
 __device__ __forceinline__ uint32_t t5_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t5_mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -50,6 +58,10 @@ __device__ __forceinline__ void t5_tma_2d(uint32_t sdst, const CUtensorMap* map,
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(sdst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void t5_tma_4d(uint32_t sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(sdst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 // K-major operand tile [128 rows][64 bf16] written by TMA with SWIZZLE_128B: 8-row groups are 1024-byte atoms
 __device__ __forceinline__ uint64_t t5_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -62,7 +74,8 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
     __shared__ uint32_t tmem_base_s;
     const uint32_t smem0 = (t5_smem(t5_raw) + 1023u) & ~1023u;                 // stage s: A at smem0 + s * 32 KB, B 16 KB after
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles_m = (p.M + T5_BM - 1) / T5_BM, tiles_n = (p.N + T5_BN - 1) / T5_BN;
+    const int tiles_xy = p.tiles_x * p.tiles_y;                                 // (conv) pixel blocks per image
+    const int tiles_m = p.conv ? (p.M / (p.H * p.W)) * tiles_xy : (p.M + T5_BM - 1) / T5_BM, tiles_n = (p.N + T5_BN - 1) / T5_BN;
     const int ntiles = tiles_m * tiles_n;
     const int nkb = (p.K + T5_BK - 1) / T5_BK;
 
@@ -95,7 +108,13 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
                     if (use > 0) t5_mbar_wait(t5_smem(&bar_empty[s]), (use - 1) & 1);
                     const uint32_t sA = smem0 + s * T5_STAGE_BYTES, sB = sA + T5_TILE_BYTES, fb = t5_smem(&bar_full[s]);
                     t5_mbar_expect(fb, T5_STAGE_BYTES);
-                    t5_tma_2d(sA, &mapA, kb * T5_BK, tm * T5_BM, fb);
+                    if (p.conv) {
+                        const int n_img = tm / tiles_xy, r = tm - n_img * tiles_xy, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                        const int tap = kb / p.cblks, cb = kb - tap * p.cblks, ky = tap / 3, kx = tap - 3 * ky;
+                        t5_tma_4d(sA, &mapA, cb * T5_BK, tx * T5_TW + kx - 1, ty * T5_TH + ky - 1, n_img, fb);
+                    } else {
+                        t5_tma_2d(sA, &mapA, kb * T5_BK, tm * T5_BM, fb);
+                    }
                     t5_tma_2d(sB, &mapB, kb * T5_BK, tn * T5_BN, fb);
                 }
             }
@@ -137,7 +156,14 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
             const uint32_t a = ti % T5_ACC, ause = ti / T5_ACC;
             t5_mbar_wait(t5_smem(&bar_acc_full[a]), ause & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = tm * T5_BM + quad * 32 + lane;
+            int row = tm * T5_BM + quad * 32 + lane;                            // output row (plain) / NHWC pixel index (conv)
+            bool row_ok = row < p.M;
+            if (p.conv) {
+                const int n_img = tm / tiles_xy, r = tm - n_img * tiles_xy, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                const int rr = quad * 32 + lane, py = ty * T5_TH + (rr >> 4), px = tx * T5_TW + (rr & 15);
+                row_ok = py < p.H && px < p.W;
+                row = (n_img * p.H + py) * p.W + px;
+            }
 #pragma unroll 1
             for (int cc = 0; cc < T5_BN / 32; ++cc) {
                 const int c0 = cc * 32;
@@ -157,7 +183,7 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
                     __syncwarp();
                     if (lane == 0) t5_mbar_arrive(t5_smem(&bar_acc_empty[a]));
                 }
-                if (row < p.M) {
+                if (row_ok) {
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
                         const int n = tn * T5_BN + c0 + j8 * 8;
@@ -165,8 +191,12 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                f[j] = rnd<bf16>(__uint_as_float(v[j8 * 8 + j]));
+                                float a = __uint_as_float(v[j8 * 8 + j]);
+                                if (p.bias) a += tof(p.bias[n + j]);
+                                f[j] = rnd<bf16>(a);
                                 if (p.act == 1) f[j] = rnd<bf16>(gelu_tanh_f(f[j]));
+                                else if (p.act == 2) f[j] = rnd<bf16>(gelu_erf_f(f[j]));
+                                if (p.scale) f[j] = rnd<bf16>(f[j] * tof(p.scale[n + j]));
                             }
                             if (p.resid) {
                                 const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + n);
@@ -216,5 +246,16 @@ static bool t5_make_map(CUtensorMap* map, const void* base, int rows, int cols, 
     const cuuint32_t box[2] = {T5_BK, T5_BM};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// NHWC bf16 tensor [N][H][W][C] as a 4-D map {C, W, H, N}; box = {64 channels, 16 x, 8 y, 1 image}, 128-byte swizzle, zero fill outside
+static bool t5_make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C) {
+    t5_encode_fn enc = t5_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {T5_BK, T5_TW, T5_TH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -117,6 +117,20 @@ __global__ void cast_to_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__
         y[i] = fromf<bf16>(tof(x[i]));
 }
 
+// nearest-neighbour x2 up-sampling of an NHWC bf16 tensor (Upsample, vq_model.py:368-379), 16 bytes per thread; C % 8 == 0
+__global__ void upsample2x_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+    const int C8 = C >> 3;
+    const long long total = (long long)B * (2 * H) * (2 * W) * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long long r = i / C8;
+        const int X = (int)(r % (2 * W)); r /= 2 * W;
+        const int Y = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        reinterpret_cast<uint4*>(y)[i] = reinterpret_cast<const uint4*>(x)[(((size_t)b * H + (Y >> 1)) * W + (X >> 1)) * C8 + c8];
+    }
+}
+
 // ---- fp32-grade path of the VQGAN encoder ("x3": split-bf16 operands, three partial products, fp32 accumulate) ----
 // VQModel.encode runs in fp32 in the reference (vq_model.py:41-46; sample / extract scripts keep the tokenizer in fp32) and its
 // arg-min indices must come out the same (index work is bit-exact), which a bf16 encoder cannot deliver: the
