@@ -21,13 +21,14 @@ from ... import engine as _engine
 
 def top_k_top_p_filtering(logits, top_k: int = 0, top_p: float = 1.0, filter_value: float = -float("Inf"),
                           min_tokens_to_keep: int = 1):
-    """Filtered copy of [B, V] logits (reference generate.py:17-56), computed by the fused sampler kernel: the
-    kept set is read back from the probabilities it returns."""
+    """Filters [B, V] logits IN PLACE and returns them, like the reference (generate.py:17-56: `logits[indices_to_remove] =
+    filter_value; return logits`); the kept set comes from the fused sampler kernel (the probabilities it returns)."""
     if min_tokens_to_keep != 1:
         raise NotImplementedError("min_tokens_to_keep != 1 is never used by ControlAR")
     sp = _engine.make_sampling(temperature=1.0, top_k=top_k, top_p=top_p, sample_logits=False, cfg_scale=1.0)
     _, probs = _engine.sample(logits, sp, return_probs=True)
-    return torch.where(probs > 0, logits, torch.full_like(logits, filter_value))
+    logits.masked_fill_(~(probs > 0), filter_value)
+    return logits
 
 
 def sample(logits, temperature: float = 1.0, top_k: int = 2000, top_p: float = 1.0, sample_logits=True,

@@ -255,9 +255,11 @@ class Transformer(nn.Module):
 
     def _sync_mask(self):
         """generate() edits ``causal_mask`` in place (reference generate.py:184-193): text columns gated by
-        emb_masks, diagonal forced.  Row T-1 of that mask holds exactly the per-sequence column gate."""
+        emb_masks, diagonal forced.  A DECODE row (position T) holds exactly the per-sequence column gate: in row T-1 the forced
+        diagonal makes column T-1 True even when emb_masks[:, T-1] == 0, while the reference's decode rows do gate it."""
         T = self.cls_token_num
-        em = self.causal_mask[:, T - 1, :T].to(torch.int32).contiguous()
+        row = T if self.causal_mask.shape[1] > T else T - 1
+        em = self.causal_mask[:, row, :T].to(torch.int32).contiguous()
         self._car_state.set_emb_mask(em)
         self._mask_synced = True
 

@@ -7,6 +7,7 @@
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
 #include "vision.cuh"
+#include "frontend.cuh"
 
 static int vis_sm_count() {
     int dev = 0, n = 148;
@@ -721,5 +722,52 @@ extern "C" int car_resize_bilinear_aa(const float* in, int32_t B, int32_t Cc, in
     const long long n1 = (long long)B * Cc * H * OW, n2 = (long long)B * Cc * OH * OW;
     CAR_LAUNCH(resize_aa_axis_kernel, (int)std::min<long long>((n1 + 255) / 256, 148 * 16), 256, 0, st, in, tmp, (long long)B * Cc * H, W, OW, 1);
     CAR_LAUNCH(resize_aa_axis_kernel, (int)std::min<long long>((n2 + 255) / 256, 148 * 16), 256, 0, st, (const float*)tmp, out, (long long)B * Cc, H, OH, OW);
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// control-map / prompt front-end (row f3): Canny edges (condition/canny.py:14) and caption left-padding (sample_t2i.py:146-156)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int64_t car_canny_workspace_bytes(int32_t H, int32_t W) {
+    const int64_t n = (int64_t)H * W;
+    return ((n * 2 + 255) / 256 * 256) * 3 + (n + 255) / 256 * 256 + 256;     // mag u16, xs i16, ys i16, map u8, changed flag
+}
+// img uint8 [H][W][C] (device) -> edges uint8 [H][W] in {0, 255}.  restart != 0: gradients + non-maximum suppression + thresholds,
+// then `sweeps` hysteresis sweeps; restart == 0: `sweeps` more sweeps on the map left in `work`.  *changed_dev (int32 in device
+// memory) is 1 afterwards iff the LAST sweep still grew an edge — the caller repeats with restart = 0 until it reads 0
+// (the reference's cv2 call is synchronous host code; here only that convergence check needs the host).
+extern "C" int car_canny_u8(const uint8_t* img, int32_t H, int32_t W, int32_t C, int32_t low, int32_t high, uint8_t* edges_out, void* work,
+                            int32_t sweeps, int32_t restart, int32_t* changed_dev, void* stream) {
+    if (!img || !edges_out || !work || !changed_dev) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (H <= 0 || W <= 0 || C <= 0 || C > 4 || sweeps < 1) CAR_FAIL(CAR_ERR_ARG, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)H * W;
+    const size_t a2 = ((size_t)n * 2 + 255) / 256 * 256;
+    unsigned short* mag = (unsigned short*)work;
+    short* xs = (short*)((char*)work + a2);
+    short* ys = (short*)((char*)work + 2 * a2);
+    unsigned char* map = (unsigned char*)work + 3 * a2;
+    if (low > high) std::swap(low, high);
+    if (restart) {
+        CAR_LAUNCH(canny_grad_kernel, gsz(n), 256, 0, st, img, H, W, C, mag, xs, ys);
+        CAR_LAUNCH(canny_nms_kernel, gsz(n), 256, 0, st, (const unsigned short*)mag, (const short*)xs, (const short*)ys, H, W, low, high, map);
+    }
+    dim3 grid((W + CH_T - 1) / CH_T, (H + CH_T - 1) / CH_T);
+    for (int s = 0; s < sweeps; ++s) {
+        CAR_CUDA(cudaMemsetAsync(changed_dev, 0, 4, st));
+        CAR_LAUNCH(canny_hyst_kernel, grid, CH_T * CH_T / 4, 0, st, map, H, W, changed_dev);
+    }
+    CAR_LAUNCH(canny_finish_kernel, gsz(n), 256, 0, st, (const unsigned char*)map, edges_out, n);
+    return CAR_OK;
+}
+
+// caption_embs [B][L][row_bytes] (any dtype, row_bytes % 16 == 0), emb_masks int64 [B][L] -> rotated embeddings + flipped masks
+extern "C" int car_left_pad_captions(const void* embs, const int64_t* masks, int32_t B, int32_t L, int32_t row_bytes, void* embs_out,
+                                     int64_t* masks_out, void* stream) {
+    if (!embs || !masks || !embs_out || !masks_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (B <= 0 || L <= 0 || row_bytes <= 0 || row_bytes % 16) CAR_FAIL(CAR_ERR_ARG, "row size must be a positive multiple of 16 bytes");
+    if (((uintptr_t)embs % 16) || ((uintptr_t)embs_out % 16)) CAR_FAIL(CAR_ERR_ARG, "embeddings must be 16-byte aligned");
+    CAR_LAUNCH(left_pad_pack_kernel, B * L, 128, 0, (cudaStream_t)stream, (const uint4*)embs, (const long long*)masks, (uint4*)embs_out,
+               (long long*)masks_out, L, row_bytes / 16);
     return CAR_OK;
 }

@@ -252,6 +252,20 @@ int car_train_destroy(CarTrain* t);
 int car_resize_bilinear_aa(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, float* out, int32_t OH, int32_t OW,
                            float* tmp, void* stream);
 
+/* ---- control-map / prompt front-end ----
+ * car_canny_u8: condition/canny.py:14 `cv2.Canny(img, low, high)` (OpenCV 4.x, aperture 3, L1 gradient) — integer arithmetic,
+ * bit-exact against OpenCV.  img uint8 [H][W][C] (C <= 4) -> edges uint8 [H][W] in {0, 255}; `work`: car_canny_workspace_bytes(H, W)
+ * bytes of device scratch.  restart != 0 computes gradients / non-maximum suppression / thresholds and runs `sweeps` hysteresis
+ * sweeps; restart == 0 runs `sweeps` more on the state in `work`.  *changed_dev (int32, device) ends 1 iff the last sweep still grew
+ * an edge: repeat with restart = 0 until it is 0 (the only host-visible check; the reference's call is synchronous host code).
+ * car_left_pad_captions: autoregressive/sample/sample_t2i.py:146-156 — valid caption tokens (a prefix) rotated to the END of the
+ * sequence, mask flipped; embs [B][L][row_bytes] of any dtype (row_bytes % 16 == 0), masks int64 [B][L]. */
+int64_t car_canny_workspace_bytes(int32_t H, int32_t W);
+int car_canny_u8(const uint8_t* img, int32_t H, int32_t W, int32_t C, int32_t low, int32_t high, uint8_t* edges_out, void* work,
+                 int32_t sweeps, int32_t restart, int32_t* changed_dev, void* stream);
+int car_left_pad_captions(const void* embs, const int64_t* masks, int32_t B, int32_t L, int32_t row_bytes, void* embs_out,
+                          int64_t* masks_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,6 +251,43 @@ def vision_512_case():
     print("vision_512 ok", tuple(out["image_fp16"].shape), float(out["enc_margin"].min()), flush=True)
 
 
+def canny_inputs():
+    """Seeded uint8 (H, W, 3) test images for the Canny front-end: pure noise, blurred noise (natural-image-like edge chains that
+    cross many 32 x 32 tiles) and a synthetic scene of ramps / discs at the real size."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    out = {}
+    out["noise_67x131"] = rng.integers(0, 256, (67, 131, 3), dtype=np.uint8)
+    k = np.array([1, 4, 6, 4, 1], dtype=np.float64); k /= k.sum()
+    def blur(a, times):
+        a = a.astype(np.float64)
+        for _ in range(times):
+            a = np.apply_along_axis(lambda v: np.convolve(np.pad(v, 2, mode="edge"), k, mode="valid"), 0, a)
+            a = np.apply_along_axis(lambda v: np.convolve(np.pad(v, 2, mode="edge"), k, mode="valid"), 1, a)
+        return np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    out["blur_200x160"] = blur(rng.integers(0, 256, (200, 160, 3)), 3)
+    yy, xx = np.mgrid[0:512, 0:512]
+    scene = np.stack([(127 + 120 * np.sin(xx / (9.0 + c) + yy / (13.0 - c))) for c in range(3)], -1)
+    scene += 60.0 * (((xx - 300) ** 2 + (yy - 200) ** 2) < 90 ** 2)[..., None]
+    scene += rng.normal(0, 6, scene.shape)
+    out["scene_512x512"] = np.clip(np.rint(scene), 0, 255).astype(np.uint8)
+    out["gray_40x56"] = blur(rng.integers(0, 256, (40, 56, 1)), 1)
+    return out
+
+
+def canny_case():
+    """cv2.Canny (the call of reference condition/canny.py:14) on the seeded images, with the reference's default thresholds and two
+    other pairs -> tests/golden/canny.npz (inputs are regenerated from the seed by the tests)."""
+    import cv2
+    import numpy as np
+    res = {"cv2_version": np.array(cv2.__version__)}
+    for name, img in canny_inputs().items():
+        for lo, hi in ((100, 200), (50, 150), (30.5, 90.7)):
+            res[f"{name}_{lo}_{hi}"] = cv2.Canny(img if img.shape[2] == 3 else img[:, :, 0], lo, hi)
+    np.savez_compressed(os.path.join(OUT, "canny.npz"), **res)
+    print("canny ok", len(res) - 1, "maps, cv2", cv2.__version__, flush=True)
+
+
 @contextlib.contextmanager
 def fake_vit_cwd(layers: int = 12):
     """vit_adapter.py:11 loads 'autoregressive/models/vit-small' relative to CWD (ViT-S/16: hidden 384, 6 heads, MLP 1536)."""
@@ -511,6 +548,7 @@ CASES = {
     "dinov2": dino_case,
     "vit": vit_case,
     "vision_512": vision_512_case,
+    "canny": canny_case,
     "c2i_gptpy_bf16": gptpy_case,
     "train_t2i_small_ac": lambda: train_case("train_t2i_small_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
                                              B=3, H=128, W=128, autocast=torch.bfloat16, use_mask=True, valid=[1, 0, 1]),

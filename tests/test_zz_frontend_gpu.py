@@ -1,0 +1,57 @@
+"""GPU: the control-map / prompt front-end through the C ABI.  Canny (reference condition/canny.py:14,
+cv2.Canny) is integer work: the CUDA path must reproduce OpenCV's maps BIT-EXACTLY (fixture made by cv2 4.13.0 + the CPU oracle);
+the caption left-padding (sample_t2i.py:146-156) against the reference's own lines."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.canny_oracle import canny as canny_oracle, left_pad_captions as left_pad_oracle
+from tests.golden.make_golden import canny_inputs
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+PAIRS = ((100, 200), (50, 150), (30.5, 90.7))
+
+
+def test_canny_bit_exact_vs_opencv_fixture():
+    from controlar_b200.condition.canny import CannyDetector, canny_cuda
+    g = np.load(f"{GOLDEN}/canny.npz")
+    det = CannyDetector()
+    for name, img in canny_inputs().items():
+        for lo, hi in PAIRS:
+            want = g[f"{name}_{lo}_{hi}"]
+            x = img if img.shape[2] == 3 else img[:, :, 0]
+            got = det(x, lo, hi)                                  # numpy in, numpy out — the reference's call
+            assert isinstance(got, np.ndarray) and got.dtype == np.uint8 and got.shape == want.shape
+            assert np.array_equal(got, want), (name, lo, hi, int((got != want).sum()))
+            got_t = canny_cuda(torch.from_numpy(np.ascontiguousarray(x)).cuda().float(), lo, hi, sweeps_per_call=1)   # device in, device out
+            assert np.array_equal(got_t.cpu().numpy(), want)
+
+
+def test_canny_large_and_non_square_vs_oracle():
+    from controlar_b200.condition.canny import canny_cuda
+    rng = np.random.default_rng(5)
+    for H, W in ((768, 512), (97, 1030)):
+        base = rng.integers(0, 256, (H // 8 + 2, W // 8 + 2, 3)).astype(np.float64)
+        img = np.kron(base, np.ones((8, 8, 1)))[:H, :W]           # blocky image: long straight edge chains across many tiles
+        img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+        want = canny_oracle(img, 100, 200)
+        got = canny_cuda(torch.from_numpy(img).cuda(), 100, 200).cpu().numpy()
+        assert np.array_equal(got, want), int((got != want).sum())
+        assert 0 < int((want > 0).sum()) < H * W
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_left_pad_captions_vs_reference_lines(dt):
+    from controlar_b200.frontend import left_pad_captions
+    g = torch.Generator().manual_seed(3)
+    B, L, D = 5, 120, 2048
+    emb = torch.randn(B, L, D, generator=g).to(dt)
+    lens = [120, 1, 37, 64, 119]
+    mask = torch.zeros(B, L, dtype=torch.int64)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    want_e, want_m = left_pad_oracle(emb, mask)
+    got_e, got_m = left_pad_captions(emb.cuda(), mask.cuda())
+    assert got_e.dtype == dt and got_m.dtype == torch.int64
+    assert torch.equal(got_e.cpu(), want_e) and torch.equal(got_m.cpu(), want_m)
