@@ -587,7 +587,8 @@ static int split3(cudaStream_t st, const float* x, bf16* y, long long npix, int 
     return CAR_OK;
 }
 // a3: S3 activations [B][Hs][Ws][3 cin_pad]; out fp32 [B][Ho][Wo][cout] (+ fp32 residual of the same shape)
-static int conv_x3(cudaStream_t st, const ConvW& c, const bf16* a3, int B, int Hs, int Ws, int stride2, float* out, const float* resid, int Ho, int Wo) {
+static int conv_x3(cudaStream_t st, const ConvW& c, const bf16* a3, int B, int Hs, int Ws, int stride2, float* out, const float* resid, int Ho, int Wo,
+                   int act = ACT_NONE) {
     if (!c.w3 || !c.bf) CAR_FAIL(CAR_ERR_STATE, "convolution has no split-bf16 weights (encoder layers only)");
     DenseP p;
     memset(&p, 0, sizeof(p));
@@ -595,7 +596,7 @@ static int conv_x3(cudaStream_t st, const ConvW& c, const bf16* a3, int B, int H
     if (c.k == 1) { p.amode = A_PLAIN; p.lda = 3 * c.cin_pad; }
     else { p.amode = stride2 ? A_CONV3x3S2 : A_CONV3x3; p.Hs = Hs; p.Ws = Ws; p.Cin = 3 * c.cin_pad; p.ups = 0; }
     p.Ho = Ho; p.Wo = Wo;
-    p.bias_f = c.bf; p.C = out; p.ldc = c.cout; p.out_mode = 1; p.resid_f = resid; p.ldr = c.cout;
+    p.bias_f = c.bf; p.C = out; p.ldc = c.cout; p.out_mode = 1; p.resid_f = resid; p.ldr = c.cout; p.act = act;
     return dense(st, p);
 }
 static int gn_x3(cudaStream_t st, const NormW& nw, const ActF& x, bf16* y3, int swish, float* stats) {
@@ -769,5 +770,110 @@ extern "C" int car_left_pad_captions(const void* embs, const int64_t* masks, int
     if (((uintptr_t)embs % 16) || ((uintptr_t)embs_out % 16)) CAR_FAIL(CAR_ERR_ARG, "embeddings must be 16-byte aligned");
     CAR_LAUNCH(left_pad_pack_kernel, B * L, 128, 0, (cudaStream_t)stream, (const uint4*)embs, (const long long*)masks, (uint4*)embs_out,
                (long long*)masks_out, L, row_bytes / 16);
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// HED soft-edge detector (row f3): condition/hed.py:17-84 — 13 ReLU 3x3 convolutions in five blocks with 2x2 max-pooling between
+// them, a 1x1 projection per block, bilinear resize of the five maps, mean, sigmoid.  fp32 in the reference => fp32-grade here.
+// ---------------------------------------------------------------------------------------------------------
+struct CarHED {
+    std::vector<void*> owned;
+    std::vector<ConvW> conv;           // 13, in forward order
+    float* norm;                       // [3]
+    float* pw[5]; float* pb[5];        // projection weights [C] / bias [1]
+    Arena ws;
+};
+static const int HED_BLK[5][3] = {{3, 64, 2}, {64, 128, 2}, {128, 256, 3}, {256, 512, 3}, {512, 512, 3}};
+
+// tensors (fp32, device), in order: norm [3]; per block: conv0.weight, conv0.bias, conv1.weight, ... , projection.weight [C], projection.bias [1]
+extern "C" int car_hed_create(const void* const* tensors, int32_t n_tensors, void* stream, CarHED** out) {
+    if (!tensors || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (n_tensors != 1 + 2 * 13 + 2 * 5) CAR_FAIL(CAR_ERR_ARG, "HED expects 37 tensors (norm, 13 x (weight, bias), 5 x (projection weight, bias))");
+    cudaStream_t st = (cudaStream_t)stream;
+    CarHED* m = new CarHED();
+    int rc = CAR_OK, ti = 0;
+    auto keep = [&](const void* src, long long n, float** dst) {
+        if (rc != CAR_OK) return;
+        if (cudaMalloc((void**)dst, (size_t)n * 4) != cudaSuccess) { rc = CAR_ERR_CUDA; g_car_err = "car_hed_create: cudaMalloc failed"; return; }
+        m->owned.push_back(*dst);
+        if (cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CAR_ERR_CUDA; g_car_err = "car_hed_create: copy failed"; }
+    };
+    keep(tensors[ti++], 3, &m->norm);
+    for (int b = 0; b < 5 && rc == CAR_OK; ++b) {
+        int cin = HED_BLK[b][0];
+        const int cout = HED_BLK[b][1];
+        for (int i = 0; i < HED_BLK[b][2] && rc == CAR_OK; ++i) {
+            ConvW c;
+            memset(&c, 0, sizeof(c));
+            c.cin = cin; c.cout = cout; c.k = 3; c.cin_pad = (cin + 31) & ~31;
+            const long long n3 = (long long)cout * 9 * c.cin_pad;
+            if (cudaMalloc((void**)&c.w3, (size_t)n3 * 3 * 2) != cudaSuccess) { rc = CAR_ERR_CUDA; g_car_err = "car_hed_create: cudaMalloc failed"; break; }
+            m->owned.push_back(c.w3);
+            conv_weight_pack_x3_kernel<<<gsz(n3), 256, 0, st>>>((const float*)tensors[ti], c.w3, cout, cin, 3, 3, c.cin_pad);
+            keep(tensors[ti + 1], cout, &c.bf);
+            ti += 2;
+            m->conv.push_back(c);
+            cin = cout;
+        }
+        keep(tensors[ti], cout, &m->pw[b]); keep(tensors[ti + 1], 1, &m->pb[b]);
+        ti += 2;
+    }
+    if (rc == CAR_OK && cudaGetLastError() != cudaSuccess) { rc = CAR_ERR_CUDA; g_car_err = "car_hed_create: weight packing failed"; }
+    if (rc != CAR_OK) { for (void* p : m->owned) cudaFree(p); delete m; return rc; }
+    *out = m;
+    return CAR_OK;
+}
+extern "C" int car_hed_destroy(CarHED* m) {
+    if (!m) return CAR_OK;
+    for (void* p : m->owned) cudaFree(p);
+    m->ws.release();
+    delete m;
+    return CAR_OK;
+}
+// image fp32 NCHW [B][3][H][W] (values 0..255) -> edge fp32 [B][H][W] in [0, 255]; proj_out (optional): the five projection maps
+// back to back, map k = [B][hk][wk] with hk = H >> k (floor), wk = W >> k
+extern "C" int car_hed_forward(CarHED* m, const float* img, int32_t B, int32_t H, int32_t W, float* edge_out, float* proj_out, void* stream) {
+    if (!m || !img || !edge_out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (B <= 0 || H < 16 || W < 16) CAR_FAIL(CAR_ERR_ARG, "image must be at least 16 x 16");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t full = (size_t)B * H * W;
+    size_t proj_elems = 0;
+    { int h = H, w = W; for (int k = 0; k < 5; ++k) { proj_elems += (size_t)B * h * w; h /= 2; w /= 2; } }
+    const size_t actf = full * 64 * 4, act3 = full * 64 * 3 * 2;                 // largest activation: 64 channels at full resolution
+    CAR_TRY(m->ws.reserve(2 * (actf + 256) + act3 + 256 + full * 32 * 3 * 2 + 256 + proj_elems * 4 + 256));
+    m->ws.reset();
+    float* fA = (float*)m->ws.take(actf); float* fB = (float*)m->ws.take(actf);
+    bf16* s3 = (bf16*)m->ws.take(act3);
+    bf16* img3 = (bf16*)m->ws.take(full * 32 * 3 * 2);
+    float* maps = (float*)m->ws.take(proj_elems * 4);
+    CAR_LAUNCH(hed_input_split3_kernel, gsz((long long)full * 32), 256, 0, st, img, (const float*)m->norm, img3, B, 3, H * W, 32);
+    HedMaps hm;
+    int h = H, w = W, ci = 0, curC = 3;
+    float* cur = nullptr;                                                       // the one live fp32 activation (NHWC); ping-pong fA / fB
+    auto other = [&](float* p) { return p == fA ? fB : fA; };
+    size_t moff = 0;
+    for (int b = 0; b < 5; ++b) {
+        if (b > 0) {                                                            // down_sampling=True (:28-30)
+            float* o = other(cur);
+            CAR_LAUNCH(maxpool2_nhwc_f32_kernel, gsz((long long)B * (h / 2) * (w / 2) * curC), 256, 0, st, (const float*)cur, o, B, h, w, curC);
+            h /= 2; w /= 2; cur = o;
+        }
+        for (int i = 0; i < HED_BLK[b][2]; ++i, ++ci) {
+            const ConvW& c = m->conv[ci];
+            const bf16* a3 = img3;
+            if (ci > 0) { CAR_TRY(split3(st, cur, s3, (long long)B * h * w, curC)); a3 = s3; }
+            float* o = other(cur);
+            CAR_TRY(conv_x3(st, c, a3, B, h, w, 0, o, nullptr, h, w, ACT_RELU));  // conv + bias, ReLU (:31-33)
+            cur = o; curC = c.cout;
+        }
+        float* mp = maps + moff;
+        CAR_LAUNCH(hed_proj_kernel, (unsigned)(((long long)B * h * w * 32 + 255) / 256), 256, 0, st, (const float*)cur, (const float*)m->pw[b], (const float*)m->pb[b], mp,
+                   (long long)B * h * w, curC);
+        hm.p[b] = mp; hm.h[b] = h; hm.w[b] = w;
+        moff += (size_t)B * h * w;
+    }
+    CAR_LAUNCH(hed_merge_kernel, gsz((long long)full), 256, 0, st, hm, B, H, W, edge_out);
+    if (proj_out) CAR_CUDA(cudaMemcpyAsync(proj_out, maps, proj_elems * 4, cudaMemcpyDeviceToDevice, st));
     return CAR_OK;
 }

@@ -117,3 +117,76 @@ __global__ void left_pad_pack_kernel(const uint4* __restrict__ in, const long lo
     uint4* d = out + ((size_t)b * L + i) * row_words;
     for (int k = threadIdx.x; k < row_words; k += blockDim.x) d[k] = s[k];
 }
+
+// ---- HED soft-edge detector (condition/hed.py:17-84), fp32 in the reference: the convolutions run on the fp32-grade split-bf16
+// path of vision.cuh ("x3"); the kernels below are the glue around them ----
+// image fp32 NCHW [B][3][HW] minus the per-channel `norm` -> S3 NHWC with Cpad channels per part (ControlNetHED_Apache2.__call__ :47)
+__global__ void hed_input_split3_kernel(const float* __restrict__ x, const float* __restrict__ norm, bf16* __restrict__ y, int B, int C, int HW, int Cpad) {
+    const long long total = (long long)B * HW * Cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const long long bp = i / Cpad;
+        const int pix = (int)(bp % HW), b = (int)(bp / HW);
+        const float v = c < C ? x[((size_t)b * C + c) * HW + pix] - norm[c] : 0.f;
+        const bf16 hi = __float2bfloat16_rn(v);
+        const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        bf16* o = y + bp * 3 * Cpad + c;
+        o[0] = hi; o[Cpad] = lo; o[2 * Cpad] = hi;
+    }
+}
+// F.max_pool2d(kernel 2, stride 2) on NHWC fp32 (floor: odd trailing rows / columns are dropped), :29-30
+__global__ void maxpool2_nhwc_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)B * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const float* p = x + (((size_t)b * H + 2 * yo) * W + 2 * xo) * C + c;
+        y[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(size_t)W * C], p[(size_t)W * C + C]));
+    }
+}
+// DoubleConvBlock.projection (1x1 convolution to ONE channel, :25,34): one warp per pixel, fp32
+__global__ void hed_proj_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ out,
+                                long long npix, int C) {
+    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pix >= npix) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(x[pix * C + c], w[c], s);
+    s = warp_sum(s);
+    if (lane == 0) out[pix] = s + b[0];
+}
+// HEDdetector.__call__ :75-78: the five projections resized to (H, W) with F.interpolate(mode='bilinear', align_corners=False),
+// averaged, sigmoid, * 255, clamped.  maps[k]: [B][hk][wk] fp32.
+struct HedMaps { const float* p[5]; int h[5], w[5]; };
+__global__ void hed_merge_kernel(HedMaps m, int B, int H, int W, float* __restrict__ out) {
+    const long long total = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long r = i / W;
+        const int y = (int)(r % H), b = (int)(r / H);
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int hk = m.h[k], wk = m.w[k];
+            const float* src = m.p[k] + (size_t)b * hk * wk;
+            float v;
+            if (hk == H && wk == W) v = src[(size_t)y * W + x];
+            else {   // ATen upsample_bilinear2d: src = max(0, scale * (dst + 0.5) - 0.5), scale = in / out
+                const float sy = fmaxf(((float)hk / (float)H) * ((float)y + 0.5f) - 0.5f, 0.f);
+                const float sx = fmaxf(((float)wk / (float)W) * ((float)x + 0.5f) - 0.5f, 0.f);
+                const int y0 = (int)sy, x0 = (int)sx;
+                const int y1 = y0 + (y0 < hk - 1 ? 1 : 0), x1 = x0 + (x0 < wk - 1 ? 1 : 0);
+                const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+                v = hy * (hx * src[(size_t)y0 * wk + x0] + lx * src[(size_t)y0 * wk + x1]) + ly * (hx * src[(size_t)y1 * wk + x0] + lx * src[(size_t)y1 * wk + x1]);
+            }
+            acc += v;
+        }
+        const float mean = acc / 5.0f;
+        const float e = 1.0f / (1.0f + expf(-mean));
+        out[i] = fminf(fmaxf(e * 255.0f, 0.f), 255.f);
+    }
+}

@@ -17,7 +17,7 @@
 #include "common.cuh"
 
 enum { A_PLAIN = 0, A_CONV3x3 = 1, A_CONV3x3S2 = 2 };
-enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_RELU = 3 };
 
 struct DenseP {
     const bf16* A; const bf16* B;
@@ -183,6 +183,7 @@ static __global__ void __launch_bounds__(DG_THREADS) dense_gemm_kernel(DenseP p)
                     if (p.out_mode == 0) v = rnd<bf16>(v);
                     if (p.act == ACT_GELU_TANH) v = rnd<bf16>(gelu_tanh_f(v));
                     else if (p.act == ACT_GELU_ERF) v = rnd<bf16>(gelu_erf_f(v));
+                    else if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
                     if (p.scale) v = rnd<bf16>(v * tof(p.scale[n]));
                     if (p.resid) v = rnd<bf16>(v + tof(p.resid[(size_t)z * p.sR + (size_t)m * p.ldr + n]));
                     if (p.out_mode == 0) ((bf16*)p.C)[(size_t)z * p.sC + (size_t)m * p.ldc + n] = fromf<bf16>(v);

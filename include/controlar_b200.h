@@ -266,6 +266,16 @@ int car_canny_u8(const uint8_t* img, int32_t H, int32_t W, int32_t C, int32_t lo
 int car_left_pad_captions(const void* embs, const int64_t* masks, int32_t B, int32_t L, int32_t row_bytes, void* embs_out,
                           int64_t* masks_out, void* stream);
 
+/* HED soft-edge detector: condition/hed.py:17-84 (ControlNetHED_Apache2 + the arithmetic of HEDdetector.__call__), fp32 in the
+ * reference => fp32-grade split-bf16 convolutions here.  car_hed_create: 37 fp32 device tensors in state-dict order — norm [3];
+ * per block b = 1..5: convs.{i}.weight [Cout][Cin][3][3], convs.{i}.bias (2, 2, 3, 3, 3 convolutions), projection.weight [C],
+ * projection.bias [1] — copied / packed (nothing borrowed).  car_hed_forward: image fp32 NCHW [B][3][H][W] in 0..255 ->
+ * edge fp32 [B][H][W] in [0, 255]; proj_out (optional) receives the five projection maps back to back ([B][H >> k][W >> k]). */
+typedef struct CarHED CarHED;
+int car_hed_create(const void* const* tensors, int32_t n_tensors, void* stream, CarHED** out);
+int car_hed_forward(CarHED* m, const float* img, int32_t B, int32_t H, int32_t W, float* edge_out, float* proj_out, void* stream);
+int car_hed_destroy(CarHED* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,3 +277,22 @@ def make_vq_state_dict(seed: int = 0, **kw) -> Dict[str, torch.Tensor]:
         else:
             out[k] = _randn(k, shp, 0.02, seed)
     return out
+
+
+# ---- HED control-map detector (condition/hed.py:17-52): procedural fp32 weights with the reference's state-dict keys ----
+HED_BLOCKS = ((3, 64, 2), (64, 128, 2), (128, 256, 3), (256, 512, 3), (512, 512, 3))
+
+
+def make_hed_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """He-scaled conv weights (activations keep their scale through the 13 ReLU convolutions), small biases, a per-channel `norm`
+    like the mean the pretrained checkpoint subtracts.  14.7 M parameters: regenerated from the seed, never stored."""
+    sd: Dict[str, torch.Tensor] = {"norm": _randn("hed.norm", (1, 3, 1, 1), 8.0, seed, mean=118.0)}
+    for b, (cin, cout, n) in enumerate(HED_BLOCKS, start=1):
+        c = cin
+        for i in range(n):
+            sd[f"block{b}.convs.{i}.weight"] = _randn(f"hed.b{b}.c{i}.w", (cout, c, 3, 3), (2.0 / (9 * c)) ** 0.5, seed)
+            sd[f"block{b}.convs.{i}.bias"] = _randn(f"hed.b{b}.c{i}.b", (cout,), 0.05, seed)
+            c = cout
+        sd[f"block{b}.projection.weight"] = _randn(f"hed.b{b}.p.w", (1, cout, 1, 1), (1.0 / cout) ** 0.5 * 0.02, seed)
+        sd[f"block{b}.projection.bias"] = _randn(f"hed.b{b}.p.b", (1,), 0.3, seed)
+    return sd

@@ -288,6 +288,38 @@ def canny_case():
     print("canny ok", len(res) - 1, "maps, cv2", cv2.__version__, flush=True)
 
 
+def hed_inputs():
+    """Seeded (B, 3, H, W) float images in 0..255 for the HED front-end: a batch whose sides divide by 16 and an odd-sized one
+    (max_pool2d floors: 70 x 90 -> 35 x 45 -> 17 x 22 -> 8 x 11 -> 4 x 5)."""
+    g = torch.Generator().manual_seed(23)
+    def img(B, H, W):
+        base = torch.rand(B, 3, H // 4 + 2, W // 4 + 2, generator=g)
+        up = torch.nn.functional.interpolate(base, size=(H, W), mode="bicubic", align_corners=False)
+        return (up * 255 + torch.randn(B, 3, H, W, generator=g) * 4).clamp(0, 255).round()
+    return {"b2_96x128": img(2, 96, 128), "b1_70x90": img(1, 70, 90)}
+
+
+def hed_case():
+    """The reference's HED detector (condition/hed.py: ControlNetHED_Apache2 + the arithmetic of HEDdetector.__call__, :69-84) in
+    fp32 on procedural weights (oracle/weights.py:make_hed_state_dict; the pretrained checkpoint is a download) -> edge maps and the
+    five projections."""
+    import types
+    from condition.hed import ControlNetHED_Apache2, HEDdetector
+    from oracle.weights import make_hed_state_dict
+    net = ControlNetHED_Apache2().float()
+    net.load_state_dict(make_hed_state_dict(seed=4), strict=True)
+    net.eval()
+    out = {"header": header(), "seed": 4}
+    fake = types.SimpleNamespace(netNetwork=net)
+    with torch.no_grad():
+        for name, x in hed_inputs().items():
+            out[name + "_edge"] = HEDdetector.__call__(fake, x).clone()
+            out[name + "_proj"] = [p.clone() for p in net(x)]
+    torch.save(out, os.path.join(OUT, "hed.pt"))
+    print("hed ok", {k: tuple(v.shape) for k, v in out.items() if k.endswith("_edge")},
+          float(out["b2_96x128_edge"].min()), float(out["b2_96x128_edge"].max()), flush=True)
+
+
 @contextlib.contextmanager
 def fake_vit_cwd(layers: int = 12):
     """vit_adapter.py:11 loads 'autoregressive/models/vit-small' relative to CWD (ViT-S/16: hidden 384, 6 heads, MLP 1536)."""
@@ -549,6 +581,7 @@ CASES = {
     "vit": vit_case,
     "vision_512": vision_512_case,
     "canny": canny_case,
+    "hed": hed_case,
     "c2i_gptpy_bf16": gptpy_case,
     "train_t2i_small_ac": lambda: train_case("train_t2i_small_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
                                              B=3, H=128, W=128, autocast=torch.bfloat16, use_mask=True, valid=[1, 0, 1]),

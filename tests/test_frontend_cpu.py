@@ -44,3 +44,17 @@ def test_left_pad_oracle_semantics():
     assert nm.tolist() == [[0, 0, 0, 1, 1], [0, 1, 1, 1, 1]]
     assert torch.equal(new[0, 3:], emb[0, :2]) and torch.equal(new[0, :3], emb[0, 2:])
     assert torch.equal(new[1, 1:], emb[1, :4]) and torch.equal(new[1, :1], emb[1, 4:])
+
+
+def test_hed_module_surface_matches_reference_keys():
+    """`controlar_b200.condition.hed.ControlNetHED_Apache2` loads a state dict with the reference's keys (condition/hed.py:37-45)."""
+    from controlar_b200.condition.hed import ControlNetHED_Apache2, HEDdetector
+    from oracle.weights import make_hed_state_dict
+    sd = make_hed_state_dict(seed=1)
+    m = ControlNetHED_Apache2()
+    assert set(m.state_dict().keys()) == set(sd.keys()) and len(sd) == 1 + 2 * 13 + 2 * 5
+    m.load_state_dict(sd, strict=True)
+    assert len(m._tensors()) == 37
+    with pytest.raises(RuntimeError):
+        m.run(torch.zeros(1, 3, 32, 32))                      # CPU tensors: no fallback path
+    assert isinstance(HEDdetector().netNetwork, ControlNetHED_Apache2)

@@ -55,3 +55,33 @@ def test_left_pad_captions_vs_reference_lines(dt):
     got_e, got_m = left_pad_captions(emb.cuda(), mask.cuda())
     assert got_e.dtype == dt and got_m.dtype == torch.int64
     assert torch.equal(got_e.cpu(), want_e) and torch.equal(got_m.cpu(), want_m)
+
+
+def test_hed_detector_vs_reference_golden():
+    """HED (reference condition/hed.py:17-84, fp32) on procedural weights: edge maps and the five projections against the fixture the
+    reference produced (tests/golden/make_golden.py:hed_case).  fp32-grade arithmetic (split-bf16 x3 convolutions): measured values go
+    to gpurun_out/hed.jsonl; bars 2e-2 of the 0..255 range for the edge map, 1e-3 relative for the projections."""
+    import json
+    import os
+    from controlar_b200.condition.hed import HEDdetector
+    from oracle.weights import make_hed_state_dict
+    from tests.golden.make_golden import hed_inputs
+    from tests.helpers import load_golden, rel_l2
+    g = load_golden("hed")
+    det = HEDdetector()
+    det.netNetwork.load_state_dict(make_hed_state_dict(seed=g["seed"]), strict=True)
+    det = det.cuda()
+    os.makedirs("gpurun_out", exist_ok=True)
+    for name, x in hed_inputs().items():
+        edge = det(x.cuda())
+        want = g[name + "_edge"]
+        assert edge.shape == want.shape and edge.dtype == torch.float32
+        err = float((edge.cpu() - want).abs().max())
+        projs = det.netNetwork(x.cuda())
+        perr = max(rel_l2(p.cpu(), q) for p, q in zip(projs, g[name + "_proj"]))
+        for p, q in zip(projs, g[name + "_proj"]):
+            assert p.shape == q.shape
+        with open(os.path.join("gpurun_out", "hed.jsonl"), "a") as fh:
+            fh.write(json.dumps({"case": name, "edge_max_abs": err, "proj_worst_rel_l2": perr, "edge_range": [float(want.min()), float(want.max())]}) + "\n")
+        assert err < 2e-2, (name, err)
+        assert perr < 1e-3, (name, perr)
