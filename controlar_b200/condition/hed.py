@@ -66,6 +66,8 @@ class ControlNetHED_Apache2(nn.Module):
         return self._h
 
     def run(self, x: torch.Tensor, want_projections: bool = False):
+        if x.device.type != "cuda":
+            raise RuntimeError("controlar_b200 HED needs CUDA tensors (no CPU path)")
         x = x.to(torch.float32).contiguous()
         B, Cc, H, W = x.shape
         assert Cc == 3, "HED takes RGB images (B, 3, H, W)"
