@@ -14,6 +14,7 @@
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
 #include "train.cuh"
+#include "t5.cuh"
 #include <algorithm>
 
 thread_local std::string g_car_err;
@@ -1130,5 +1131,79 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
     } else if (logits_out) {
         CAR_LAUNCH(tr_put_rows_bf16_kernel, tr_grid((long long)RC * V), 256, 0, st, (const bf16*)t->lg, logits_out, 1, RC, RC, 0, V);
     }
+    return CAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// T5 text encoder forward: language/t5.py:58-79 -> HF T5EncoderModel(...).last_hidden_state, bf16.
+// v1.1 / flan architecture: gated gelu_new feed-forward, no biases, RMS layer norm (eps 1e-6), relative position bias of block 0
+// shared by every block, no 1/sqrt(d) scaling.  GEMMs: dense_linear (tcgen05); glue: t5.cuh.
+// ---------------------------------------------------------------------------------------------------------
+struct CarT5 {
+    CarT5Desc d;
+    const void *embed, *rel_bias, *final_norm;
+    std::vector<const void*> ln1, wq, wk, wv, wo, ln2, wi0, wi1, wo2;
+    int max_rows;
+    bf16 *h, *x, *q, *k, *v, *att, *g, *u, *act;
+    std::vector<void*> owned;
+};
+
+extern "C" int car_t5_create(const CarT5Desc* desc, const CarT5Weights* w, int32_t max_rows, void* stream, CarT5** out) {
+    if (!desc || !w || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    (void)stream;
+    const CarT5Desc& d = *desc;
+    if (d.dtype != CAR_BF16) CAR_FAIL(CAR_ERR_UNSUPPORTED, "the T5 encoder is built for bf16 checkpoints (the reference's default torch_dtype, language/t5.py:22)");
+    if (d.d_kv != 64 || d.d_model % 8 || d.d_ff % 8 || d.n_heads <= 0 || d.n_layers <= 0 || max_rows <= 0 || d.num_buckets % 2)
+        CAR_FAIL(CAR_ERR_UNSUPPORTED, "shape not supported (d_kv 64, dims multiple of 8)");
+    CarT5* t = new CarT5();
+    t->d = d; t->embed = w->embed; t->rel_bias = w->rel_bias; t->final_norm = w->final_norm; t->max_rows = max_rows;
+    const int L = d.n_layers;
+    auto cp = [&](std::vector<const void*>& v, const void* const* src) { v.assign(src, src + L); };
+    cp(t->ln1, w->ln1); cp(t->wq, w->q); cp(t->wk, w->k); cp(t->wv, w->v); cp(t->wo, w->o); cp(t->ln2, w->ln2);
+    cp(t->wi0, w->wi_0); cp(t->wi1, w->wi_1); cp(t->wo2, w->wo);
+    const size_t R = (size_t)max_rows, inner = (size_t)d.n_heads * 64;
+    int rc = CAR_OK;
+    auto A = [&](bf16** p, size_t elems) { if (rc == CAR_OK) rc = alloc_dev(t->owned, (void**)p, elems * 2); };
+    A(&t->h, R * d.d_model); A(&t->x, R * d.d_model); A(&t->q, R * inner); A(&t->k, R * inner); A(&t->v, R * inner); A(&t->att, R * inner);
+    A(&t->g, R * d.d_ff); A(&t->u, R * d.d_ff); A(&t->act, R * d.d_ff);
+    if (rc != CAR_OK) { for (void* p : t->owned) cudaFree(p); delete t; return rc; }
+    *out = t;
+    return CAR_OK;
+}
+extern "C" int car_t5_destroy(CarT5* t) {
+    if (!t) return CAR_OK;
+    for (void* p : t->owned) cudaFree(p);
+    delete t;
+    return CAR_OK;
+}
+// ids int32 [B][L], mask int32 [B][L] (1 = token, 0 = padding) -> last_hidden_state bf16 [B][L][d_model]
+extern "C" int car_t5_forward(CarT5* t, const int32_t* ids, const int32_t* mask, int32_t B, int32_t L, void* out, void* stream) {
+    if (!t || !ids || !mask || !out) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (B <= 0 || L <= 0 || (long long)B * L > t->max_rows) CAR_FAIL(CAR_ERR_ARG, "batch x length beyond the capacity given to car_t5_create");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CarT5Desc& d = t->d;
+    const int R = B * L, dm = d.d_model, inner = d.n_heads * 64, F = d.d_ff;
+    const size_t att_smem = (size_t)T5A_WARPS * L * 4;
+    if (att_smem > 48 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "sequence too long for the T5 attention kernel (L <= 3072)");
+    CAR_LAUNCH(t5_embed_kernel, R, 128, 0, st, (const int*)ids, (const bf16*)t->embed, t->h, R, dm);
+    for (int l = 0; l < d.n_layers; ++l) {
+        // T5LayerSelfAttention (modeling_t5.py: layer_norm -> SelfAttention -> residual)
+        CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), R, 256, 0, st, (const bf16*)t->h, (const bf16*)t->ln1[l], t->x, dm, d.eps);
+        CAR_TRY(dense_linear(st, t->x, dm, t->wq[l], R, inner, dm, ACT_NONE, nullptr, 0, t->q, inner));
+        CAR_TRY(dense_linear(st, t->x, dm, t->wk[l], R, inner, dm, ACT_NONE, nullptr, 0, t->k, inner));
+        CAR_TRY(dense_linear(st, t->x, dm, t->wv[l], R, inner, dm, ACT_NONE, nullptr, 0, t->v, inner));
+        CAR_LAUNCH(t5_attention_kernel, (unsigned)(((long long)B * d.n_heads * L + T5A_WARPS - 1) / T5A_WARPS), T5A_WARPS * 32, att_smem, st,
+                   (const bf16*)t->q, (const bf16*)t->k, (const bf16*)t->v, (const bf16*)t->rel_bias, (const int*)mask, B, d.n_heads, L, d.num_buckets,
+                   d.max_distance, t->att);
+        CAR_TRY(dense_linear(st, t->att, inner, t->wo[l], R, dm, inner, ACT_NONE, t->h, dm, t->h, dm));          // hidden + attention_output
+        // T5LayerFF: layer_norm -> wi_0 / wi_1 -> gelu_new(.) * . -> wo -> residual
+        CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), R, 256, 0, st, (const bf16*)t->h, (const bf16*)t->ln2[l], t->x, dm, d.eps);
+        CAR_TRY(dense_linear(st, t->x, dm, t->wi0[l], R, F, dm, ACT_NONE, nullptr, 0, t->g, F));
+        CAR_TRY(dense_linear(st, t->x, dm, t->wi1[l], R, F, dm, ACT_NONE, nullptr, 0, t->u, F));
+        CAR_LAUNCH(t5_geglu_kernel, (int)std::min<long long>(((long long)R * F + 255) / 256, 148 * 16), 256, 0, st, (const bf16*)t->g, (const bf16*)t->u, t->act,
+                   (long long)R * F);
+        CAR_TRY(dense_linear(st, t->act, F, t->wo2[l], R, dm, F, ACT_NONE, t->h, dm, t->h, dm));
+    }
+    CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), R, 256, 0, st, (const bf16*)t->h, (const bf16*)t->final_norm, (bf16*)out, dm, d.eps);
     return CAR_OK;
 }

@@ -276,6 +276,31 @@ int car_hed_create(const void* const* tensors, int32_t n_tensors, void* stream, 
 int car_hed_forward(CarHED* m, const float* img, int32_t B, int32_t H, int32_t W, float* edge_out, float* proj_out, void* stream);
 int car_hed_destroy(CarHED* m);
 
+/* T5 text encoder: language/t5.py:58-79 — HF T5EncoderModel(input_ids, attention_mask).last_hidden_state in
+ * bf16 (v1.1 / flan architecture: gated gelu_new feed-forward, no biases, RMS layer norm, relative position bias of block 0 shared
+ * by all blocks, no 1/sqrt(d) scaling).  Weights ([out, in] row-major bf16, HF state-dict tensors) are borrowed until
+ * car_t5_destroy; workspaces hold max_rows = B * L token rows. */
+typedef struct CarT5 CarT5;
+typedef struct CarT5Desc {
+    int32_t dtype;             /* CAR_BF16 */
+    int32_t d_model, d_kv, n_heads, d_ff, n_layers, vocab;
+    int32_t num_buckets, max_distance;   /* relative_attention_num_buckets (32), relative_attention_max_distance (128) */
+    float   eps;               /* layer_norm_epsilon (1e-6) */
+} CarT5Desc;
+typedef struct CarT5Weights {
+    const void* embed;         /* shared.weight [vocab, d_model] */
+    const void* rel_bias;      /* encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight [num_buckets, n_heads] */
+    const void* final_norm;    /* encoder.final_layer_norm.weight [d_model] */
+    const void* const* ln1;    /* per block: layer.0.layer_norm.weight */
+    const void* const* q; const void* const* k; const void* const* v; const void* const* o;   /* layer.0.SelfAttention.{q,k,v,o}.weight */
+    const void* const* ln2;    /* layer.1.layer_norm.weight */
+    const void* const* wi_0; const void* const* wi_1; const void* const* wo;                  /* layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight */
+} CarT5Weights;
+int car_t5_create(const CarT5Desc* desc, const CarT5Weights* weights, int32_t max_rows, void* stream, CarT5** out);
+/* ids int32 [B, L], mask int32 [B, L] (1 = token) -> out bf16 [B, L, d_model] */
+int car_t5_forward(CarT5* t, const int32_t* ids, const int32_t* mask, int32_t B, int32_t L, void* out, void* stream);
+int car_t5_destroy(CarT5* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -296,3 +296,24 @@ def make_hed_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
         sd[f"block{b}.projection.weight"] = _randn(f"hed.b{b}.p.w", (1, cout, 1, 1), (1.0 / cout) ** 0.5 * 0.02, seed)
         sd[f"block{b}.projection.bias"] = _randn(f"hed.b{b}.p.b", (1,), 0.3, seed)
     return sd
+
+
+# ---- T5 text encoder (language/t5.py:54 -> HF T5EncoderModel, v1.1 / flan architecture): procedural weights with the HF keys ----
+def make_t5_state_dict(d_model: int, d_kv: int, num_heads: int, d_ff: int, num_layers: int, vocab: int, num_buckets: int = 32,
+                       seed: int = 0) -> Dict[str, torch.Tensor]:
+    inner = d_kv * num_heads
+    sd: Dict[str, torch.Tensor] = {"shared.weight": _randn("t5.shared", (vocab, d_model), 1.0, seed)}
+    sd["encoder.embed_tokens.weight"] = sd["shared.weight"]
+    sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"] = _randn("t5.relbias", (num_buckets, num_heads), 0.5, seed)
+    for i in range(num_layers):
+        p = f"encoder.block.{i}."
+        for n, shp, std in (("q", (inner, d_model), (d_model * d_kv) ** -0.5), ("k", (inner, d_model), d_model ** -0.5),
+                            ("v", (inner, d_model), d_model ** -0.5), ("o", (d_model, inner), inner ** -0.5)):
+            sd[p + f"layer.0.SelfAttention.{n}.weight"] = _randn(f"t5.{i}.{n}", shp, std * 1.5, seed)
+        sd[p + "layer.0.layer_norm.weight"] = _randn(f"t5.{i}.ln1", (d_model,), 0.1, seed, mean=1.0)
+        sd[p + "layer.1.DenseReluDense.wi_0.weight"] = _randn(f"t5.{i}.wi0", (d_ff, d_model), d_model ** -0.5, seed)
+        sd[p + "layer.1.DenseReluDense.wi_1.weight"] = _randn(f"t5.{i}.wi1", (d_ff, d_model), d_model ** -0.5, seed)
+        sd[p + "layer.1.DenseReluDense.wo.weight"] = _randn(f"t5.{i}.wo", (d_model, d_ff), d_ff ** -0.5, seed)
+        sd[p + "layer.1.layer_norm.weight"] = _randn(f"t5.{i}.ln2", (d_model,), 0.1, seed, mean=1.0)
+    sd["encoder.final_layer_norm.weight"] = _randn("t5.fn", (d_model,), 0.1, seed, mean=1.0)
+    return sd

@@ -320,6 +320,45 @@ def hed_case():
           float(out["b2_96x128_edge"].min()), float(out["b2_96x128_edge"].max()), flush=True)
 
 
+T5_SMALL = dict(d_model=256, d_kv=64, num_heads=4, d_ff=640, num_layers=3, vocab=512)
+
+
+def t5_inputs():
+    """Seeded (input_ids, attention_mask) batches: right-padded prompts like the T5 tokenizer produces (pad id 0), incl. a one-token
+    prompt, and a 160-token one whose relative distances exceed relative_attention_max_distance = 128."""
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    for name, (B, L, lens) in {"b3_L24": (3, 24, [24, 9, 1]), "b2_L120": (2, 120, [120, 37]), "b1_L160": (1, 160, [160])}.items():
+        ids = torch.randint(2, T5_SMALL["vocab"], (B, L), generator=g)
+        mask = torch.zeros(B, L, dtype=torch.int64)
+        for b, n in enumerate(lens):
+            mask[b, :n] = 1
+        out[name] = (ids * mask, mask)
+    return out
+
+
+def t5_case():
+    """HF T5EncoderModel (the model behind the reference's language/t5.py:54,69-75) in bf16 on procedural weights, v1.1 / flan
+    architecture at a small size -> last_hidden_state."""
+    from transformers import T5Config, T5EncoderModel
+    from oracle.weights import make_t5_state_dict
+    c = T5_SMALL
+    cfg = T5Config(vocab_size=c["vocab"], d_model=c["d_model"], d_kv=c["d_kv"], d_ff=c["d_ff"], num_layers=c["num_layers"], num_heads=c["num_heads"],
+                   relative_attention_num_buckets=32, relative_attention_max_distance=128, feed_forward_proj="gated-gelu",
+                   layer_norm_epsilon=1e-6, dropout_rate=0.0, tie_word_embeddings=False)
+    model = T5EncoderModel(cfg)
+    missing, unexpected = model.load_state_dict(make_t5_state_dict(**c, seed=6), strict=False)
+    assert not unexpected and all("embed_tokens" in m or "shared" in m for m in missing), (missing, unexpected)
+    model = model.to(torch.bfloat16).eval()
+    assert cfg.dense_act_fn == "gelu_new" and cfg.is_gated_act
+    out = {"header": header(), "seed": 6, "config": dict(c)}
+    with torch.no_grad():
+        for name, (ids, mask) in t5_inputs().items():
+            out[name] = model(input_ids=ids, attention_mask=mask)["last_hidden_state"].clone()
+    torch.save(out, os.path.join(OUT, "t5.pt"))
+    print("t5 ok", {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")}, float(out["b3_L24"].float().abs().mean()), flush=True)
+
+
 @contextlib.contextmanager
 def fake_vit_cwd(layers: int = 12):
     """vit_adapter.py:11 loads 'autoregressive/models/vit-small' relative to CWD (ViT-S/16: hidden 384, 6 heads, MLP 1536)."""
@@ -582,6 +621,7 @@ CASES = {
     "vision_512": vision_512_case,
     "canny": canny_case,
     "hed": hed_case,
+    "t5": t5_case,
     "c2i_gptpy_bf16": gptpy_case,
     "train_t2i_small_ac": lambda: train_case("train_t2i_small_ac", GPTSpec(**SMALL, cls_token_num=120, block_size=64, model_type="t2i"),
                                              B=3, H=128, W=128, autocast=torch.bfloat16, use_mask=True, valid=[1, 0, 1]),

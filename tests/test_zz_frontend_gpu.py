@@ -85,3 +85,32 @@ def test_hed_detector_vs_reference_golden():
             fh.write(json.dumps({"case": name, "edge_max_abs": err, "proj_worst_rel_l2": perr, "edge_range": [float(want.min()), float(want.max())]}) + "\n")
         assert err < 2e-2, (name, err)
         assert perr < 1e-3, (name, perr)
+
+
+def test_t5_encoder_vs_hf_golden():
+    """T5 encoder forward (reference language/t5.py:69-75 -> HF T5EncoderModel, bf16) against the fixture HF itself produced on
+    procedural weights (tests/golden/make_golden.py:t5_case): right-padded prompts, a one-token prompt, distances beyond the
+    relative-position clamp.  bf16 against bf16: rel-L2 per case logged to gpurun_out/t5.jsonl, bar 1e-2."""
+    import json
+    import os
+    from controlar_b200.language.t5 import T5EncoderB200
+    from oracle.weights import make_t5_state_dict
+    from tests.golden.make_golden import t5_inputs
+    from tests.helpers import load_golden, rel_l2
+    g = load_golden("t5")
+    c = g["config"]
+    sd = {k: v.to(torch.bfloat16) for k, v in make_t5_state_dict(**c, seed=g["seed"]).items()}
+    enc = T5EncoderB200(sd, d_model=c["d_model"], d_kv=c["d_kv"], num_heads=c["num_heads"], d_ff=c["d_ff"], num_layers=c["num_layers"],
+                        vocab_size=c["vocab"], max_rows=64)
+    os.makedirs("gpurun_out", exist_ok=True)
+    for name, (ids, mask) in t5_inputs().items():
+        out = enc(input_ids=ids.cuda(), attention_mask=mask.cuda())["last_hidden_state"]
+        want = g[name]
+        assert out.shape == want.shape and out.dtype == torch.bfloat16
+        err = rel_l2(out.float().cpu(), want.float())
+        exact = float((out.cpu() == want).float().mean())
+        with open(os.path.join("gpurun_out", "t5.jsonl"), "a") as fh:
+            fh.write(json.dumps({"case": name, "rel_l2": err, "bit_identical_fraction": exact}) + "\n")
+        assert err < 1e-2, (name, err)
+    out2 = enc(input_ids=ids.cuda(), attention_mask=mask.cuda())["last_hidden_state"]
+    assert torch.equal(out, out2)
