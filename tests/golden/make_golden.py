@@ -352,11 +352,16 @@ def t5_case():
     model = model.to(torch.bfloat16).eval()
     assert cfg.dense_act_fn == "gelu_new" and cfg.is_gated_act
     out = {"header": header(), "seed": 6, "config": dict(c)}
+    # the same bf16-rounded weights evaluated in fp32: the exact result both bf16 evaluations (HF's and the CUDA path's) approximate
+    exact = T5EncoderModel(cfg)
+    exact.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in make_t5_state_dict(**c, seed=6).items()}, strict=False)
+    exact.eval()
     with torch.no_grad():
         for name, (ids, mask) in t5_inputs().items():
             out[name] = model(input_ids=ids, attention_mask=mask)["last_hidden_state"].clone()
+            out[name + "_fp32"] = exact(input_ids=ids, attention_mask=mask)["last_hidden_state"].to(torch.float16).clone()
     torch.save(out, os.path.join(OUT, "t5.pt"))
-    print("t5 ok", {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")}, float(out["b3_L24"].float().abs().mean()), flush=True)
+    print("t5 ok", {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape") and not k.endswith("_fp32")}, float(out["b3_L24"].float().abs().mean()), flush=True)
 
 
 @contextlib.contextmanager

@@ -90,7 +90,10 @@ def test_hed_detector_vs_reference_golden():
 def test_t5_encoder_vs_hf_golden():
     """T5 encoder forward (reference language/t5.py:69-75 -> HF T5EncoderModel, bf16) against the fixture HF itself produced on
     procedural weights (tests/golden/make_golden.py:t5_case): right-padded prompts, a one-token prompt, distances beyond the
-    relative-position clamp.  bf16 against bf16: rel-L2 per case logged to gpurun_out/t5.jsonl, bar 1e-2."""
+    relative-position clamp.  Two bf16 evaluations of the same network differ by rounding order: HF's own bf16 output sits
+    1.3e-2 ... 2.2e-2 (rel-L2) from the fp32 evaluation of the same weights (stored in the fixture), so the bars are (a) at most
+    2.5e-2 from HF's bf16 output and (b) at least as close to the fp32 result as HF's bf16 output is (x 1.25).  Values are logged
+    to gpurun_out/t5.jsonl."""
     import json
     import os
     from controlar_b200.language.t5 import T5EncoderB200
@@ -108,9 +111,11 @@ def test_t5_encoder_vs_hf_golden():
         want = g[name]
         assert out.shape == want.shape and out.dtype == torch.bfloat16
         err = rel_l2(out.float().cpu(), want.float())
-        exact = float((out.cpu() == want).float().mean())
+        exact = g[name + "_fp32"].float()
+        err_exact, hf_exact = rel_l2(out.float().cpu(), exact), rel_l2(want.float(), exact)
         with open(os.path.join("gpurun_out", "t5.jsonl"), "a") as fh:
-            fh.write(json.dumps({"case": name, "rel_l2": err, "bit_identical_fraction": exact}) + "\n")
-        assert err < 1e-2, (name, err)
+            fh.write(json.dumps({"case": name, "rel_l2_vs_hf_bf16": err, "rel_l2_vs_fp32": err_exact, "hf_bf16_vs_fp32": hf_exact}) + "\n")
+        assert err < 2.5e-2, (name, err)
+        assert err_exact < 1.25 * hf_exact, (name, err_exact, hf_exact)
     out2 = enc(input_ids=ids.cuda(), attention_mask=mask.cuda())["last_hidden_state"]
     assert torch.equal(out, out2)
