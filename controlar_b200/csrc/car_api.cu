@@ -517,6 +517,16 @@ static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, 
         memset(&q, 0, sizeof(q));
         q.M = M; q.N = N; q.K = K;
         q.resid = (const bf16*)resid; q.ldr = ldr; q.C = (bf16*)out; q.ldc = ldo; q.act = act == ACT_GELU_TANH ? 1 : 0;
+        static const bool use_x2 = [] { const char* e = getenv("CAR_TC5X2"); return e ? atoi(e) != 0 : true; }();
+        if (use_x2 && M >= T2_BM && N >= T2_BN) {
+            // 2-CTA tiles (cta_group::2, 256 x 256 per CTA pair): twice the math per operand byte pulled from L2
+            static DevOnce once52;
+            if (once52.first()) CAR_CUDA(cudaFuncSetAttribute(gemm_tc5x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+            const int ptiles = ((M + T2_BM - 1) / T2_BM) * ((N + T2_BN - 1) / T2_BN);
+            const int pairs = std::max(1, std::min(ptiles, sm_count() / 2));
+            CAR_LAUNCH(gemm_tc5x2_kernel, 2 * pairs, T5_THREADS, T5_SMEM, st, mapA, mapB, q);
+            return CAR_OK;
+        }
         const int ntiles = ((M + T5_BM - 1) / T5_BM) * ((N + T5_BN - 1) / T5_BN);
         CAR_LAUNCH(gemm_tc5_kernel, std::min(ntiles, sm_count()), T5_THREADS, T5_SMEM, st, mapA, mapB, q);
         return CAR_OK;

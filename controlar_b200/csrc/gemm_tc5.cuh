@@ -225,6 +225,182 @@ static __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// =========================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one TPC) computes a 256 x 256 output tile.  Each CTA loads ITS half of both
+// operands per 64-wide k-block — A rows [m0 + 128 rank, +128), B rows [n0 + 128 rank, +128) — and the leader CTA issues
+// tcgen05.mma.cta_group::2 (UMMA M = 256, N = 256): every tensor core reads its own A half and BOTH B halves, so each SM does
+// twice the math of the 1-CTA tile per byte it pulls from L2 (128 instead of 64 FLOP per operand byte: the 1-CTA kernel is bounded
+// by L2 -> SM operand bandwidth, measured 543 TFLOP/s on M1920 N3584 K1280 against cuBLAS' 1019).  Accumulators: 128 lanes x 256
+// fp32 columns per CTA and stage, two stages = all 512 TMEM columns.  Barriers live in the leader's shared memory for the
+// TMA -> MMA direction (both CTAs' TMA loads complete_tx on the leader's full[s], address with the peer bit cleared) and are
+// multicast to both CTAs for the MMA -> producer / MMA -> epilogue direction (tcgen05.commit ... multicast::cluster).
+// =========================================================================================================
+constexpr int T2_BM = 256, T2_BN = 256;
+__device__ __forceinline__ void t5_tma_2d_2cta(uint32_t sdst, const CUtensorMap* map, int c0, int c1, uint32_t bar_leader) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(sdst), "l"(map), "r"(c0), "r"(c1), "r"(bar_leader) : "memory");
+}
+__device__ __forceinline__ void t5_commit_2cta(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void t5_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T5_THREADS, 1)
+gemm_tc5x2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Tc5P p) {
+    extern __shared__ unsigned char t5_raw[];
+    __shared__ __align__(8) uint64_t bar_full[T5_STAGES], bar_empty[T5_STAGES], bar_acc_full[T5_ACC], bar_acc_empty[T5_ACC];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t smem0 = (t5_smem(t5_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int tiles_m = (p.M + T2_BM - 1) / T2_BM, tiles_n = (p.N + T2_BN - 1) / T2_BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int nkb = (p.K + T5_BK - 1) / T5_BK;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < T5_STAGES; ++s) { t5_mbar_init(t5_smem(&bar_full[s]), 1); t5_mbar_init(t5_smem(&bar_empty[s]), 1); }
+        for (int a = 0; a < T5_ACC; ++a) { t5_mbar_init(t5_smem(&bar_acc_full[a]), 1); t5_mbar_init(t5_smem(&bar_acc_empty[a]), 8); }   // 4 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(t5_smem(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    t5_cluster_sync();                                   // both CTAs' barriers are initialised before any remote arrive / TMA signal
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs): own halves of A and B, completion on the LEADER's full barrier =====
+            uint32_t it = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                const int tm = t % tiles_m, tn = t / tiles_m;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % T5_STAGES, use = it / T5_STAGES;
+                    if (use > 0) t5_mbar_wait(t5_smem(&bar_empty[s]), (use - 1) & 1);
+                    const uint32_t sA = smem0 + s * T5_STAGE_BYTES, sB = sA + T5_TILE_BYTES;
+                    const uint32_t fb = t5_smem(&bar_full[s]);
+                    if (leader) t5_mbar_expect(fb, 2 * T5_STAGE_BYTES);            // 4 tiles of 16 KB: two from each CTA
+                    uint32_t fb_leader;                                            // the same barrier in the leader CTA (rank 0) of the pair
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fb_leader) : "r"(fb), "r"(0));
+                    t5_tma_2d_2cta(sA, &mapA, kb * T5_BK, tm * T2_BM + (int)rank * 128, fb_leader);
+                    t5_tma_2d_2cta(sB, &mapB, kb * T5_BK, tn * T2_BN + (int)rank * 128, fb_leader);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===== MMA issuer (leader CTA only) =====
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters, ++ti) {
+                const uint32_t a = ti % T5_ACC, ause = ti / T5_ACC;
+                if (ause > 0) t5_mbar_wait(t5_smem(&bar_acc_empty[a]), (ause - 1) & 1);        // both CTAs' epilogues drained this stage
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + a * T2_BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % T5_STAGES, use = it / T5_STAGES;
+                    t5_mbar_wait(t5_smem(&bar_full[s]), use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sA = smem0 + s * T5_STAGE_BYTES, sB = sA + T5_TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < T5_BK / 16; ++kk) {
+                        const uint64_t da = t5_desc_sw128(sA + kk * 32), db = t5_desc_sw128(sB + kk * 32);
+                        const uint32_t accf = (kb > 0 || kk > 0) ? 1u : 0u;
+                        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                     ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+                    }
+                    t5_commit_2cta(t5_smem(&bar_empty[s]));                        // frees stage s in BOTH CTAs
+                }
+                t5_commit_2cta(t5_smem(&bar_acc_full[a]));                         // wakes both CTAs' epilogue warps
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 of both CTAs: this CTA's 128 rows x 256 columns =====
+        const int quad = warp & 3;
+        uint32_t acc_empty_leader[T5_ACC];
+#pragma unroll
+        for (int a = 0; a < T5_ACC; ++a)
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(acc_empty_leader[a]) : "r"(t5_smem(&bar_acc_empty[a])), "r"(0));
+        uint32_t ti = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters, ++ti) {
+            const int tm = t % tiles_m, tn = t / tiles_m;
+            const uint32_t a = ti % T5_ACC, ause = ti / T5_ACC;
+            t5_mbar_wait(t5_smem(&bar_acc_full[a]), ause & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = tm * T2_BM + (int)rank * 128 + quad * 32 + lane;
+#pragma unroll 1
+            for (int cc = 0; cc < T2_BN / 32; ++cc) {
+                const int c0 = cc * 32;
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * T2_BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                    "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                      "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == T2_BN / 32 - 1) {                        // the whole accumulator stage is in registers: release it (to the leader)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader[a]) : "memory");
+                }
+                if (row < p.M) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const int n = tn * T2_BN + c0 + j8 * 8;
+                        if (n < p.N) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float x = __uint_as_float(v[j8 * 8 + j]);
+                                if (p.bias) x += tof(p.bias[n + j]);
+                                f[j] = rnd<bf16>(x);
+                                if (p.act == 1) f[j] = rnd<bf16>(gelu_tanh_f(f[j]));
+                                else if (p.act == 2) f[j] = rnd<bf16>(gelu_erf_f(f[j]));
+                                if (p.scale) f[j] = rnd<bf16>(f[j] * tof(p.scale[n + j]));
+                            }
+                            if (p.resid) {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + n);
+                                const uint32_t ri[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    float x, y;
+                                    unpack_bf16x2(ri[q], x, y);
+                                    f[2 * q] = rnd<bf16>(f[2 * q] + x); f[2 * q + 1] = rnd<bf16>(f[2 * q + 1] + y);
+                                }
+                            }
+                            uint4 o;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                            o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+                            o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+                            *reinterpret_cast<uint4*>(p.C + (size_t)row * p.ldc + n) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    t5_cluster_sync();                                   // no CTA frees TMEM / exits while its partner still reads its shared memory
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 // ---- host: tensor maps (driver entry point fetched through the runtime: the library does not link libcuda) ----
 typedef CUresult (*t5_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
