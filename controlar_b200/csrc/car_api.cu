@@ -518,12 +518,15 @@ static int dense_linear(cudaStream_t st, const void* A, int lda, const void* W, 
         q.M = M; q.N = N; q.K = K;
         q.resid = (const bf16*)resid; q.ldr = ldr; q.C = (bf16*)out; q.ldc = ldo; q.act = act == ACT_GELU_TANH ? 1 : 0;
         static const bool use_x2 = [] { const char* e = getenv("CAR_TC5X2"); return e ? atoi(e) != 0 : true; }();
-        if (use_x2 && M >= T2_BM && N >= T2_BN) {
-            // 2-CTA tiles (cta_group::2, 256 x 256 per CTA pair): twice the math per operand byte pulled from L2
+        // 2-CTA tiles (cta_group::2, 256 x 256 per CTA pair): twice the math per operand byte pulled from L2.  Measured (B200,
+        // scripts/bench_gemm.py, TFLOP/s 1-CTA -> 2-CTA): 8192^3 894 -> 1345; 16384 x 1280 x 1280 700 -> 870; 1920 x 3840 x 1280
+        // 503 -> 598; 1920 x 3584 x 1280 546 -> 554; but 1920 x 1280 x 3584 (40 pair tiles on 74 pairs) 375 -> 265: with fewer
+        // pair tiles than ~1.3 waves the coarser tiling idles SMs, so small grids stay on the 128 x 128 kernel.
+        const int ptiles_x2 = ((M + T2_BM - 1) / T2_BM) * ((N + T2_BN - 1) / T2_BN);
+        if (use_x2 && M >= T2_BM && N >= T2_BN && ptiles_x2 >= 100) {
             static DevOnce once52;
             if (once52.first()) CAR_CUDA(cudaFuncSetAttribute(gemm_tc5x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
-            const int ptiles = ((M + T2_BM - 1) / T2_BM) * ((N + T2_BN - 1) / T2_BN);
-            const int pairs = std::max(1, std::min(ptiles, sm_count() / 2));
+            const int pairs = std::max(1, std::min(ptiles_x2, sm_count() / 2));
             CAR_LAUNCH(gemm_tc5x2_kernel, 2 * pairs, T5_THREADS, T5_SMEM, st, mapA, mapB, q);
             return CAR_OK;
         }
