@@ -348,26 +348,27 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
     for_kept([&](int, float z) { mass += __float2ull_rn(expf(z - mx) * SMP_FIX); });
     mass = smp_block_sum64<THREADS>(mass, red_q);
     float sum = (float)mass * (1.0f / SMP_FIX);
-    // ---- nucleus (top-p), generate.py:40-55: in descending order a token is removed iff the cumulative probability
-    // of the tokens strictly before it exceeds top_p (first always kept).  Equivalently token x is kept iff
-    // f(p_x) <= top_p with f(v) = mass of tokens with probability > v; f is a non-increasing step function, so the
-    // kept set is {p >= tau*}; tau* is bracketed by 30 bisection steps (tokens within 2^-30 of the boundary count as
-    // ties and are kept; torch.sort's order among exact ties is unspecified anyway).
+    // ---- nucleus (top-p), generate.py:40-55: in descending order a token is removed iff the cumulative probability of the tokens
+    // strictly before it exceeds top_p (first always kept).  Equivalently token x is kept iff f(p_x) <= top_p with f(v) = mass of the
+    // tokens with probability > v; f is a non-increasing step function, so the kept set is {p >= tau*} with tau* the SMALLEST
+    // probability that satisfies it.  tau* is found exactly by a 32-step binary search over the order-preserving integer keys of the
+    // probabilities (a bisection on the value with a fixed step count kept tokens within 2^-30 of the boundary), the masses
+    // compared in 64-bit fixed point.  (torch.sort's order among exactly tied probabilities is unspecified; ties are kept together.)
     const float sum_pre = sum;                             // normaliser of the pre-nucleus probabilities
-    float p_lo = -1.f;                                     // elements with pre-nucleus probability <= p_lo are dropped (none by default)
+    unsigned p_key = 0u;                                   // elements whose pre-nucleus probability key is below p_key are dropped
     if (a.top_p < 1.0f) {
-        float lo = 0.f, hi = 1.0f;                         // f(lo) > top_p >= f(hi)
         const double budget = (double)a.top_p * (double)mass;
-        for (int it = 0; it < 30; ++it) {
-            const float mid = 0.5f * (lo + hi);
+        unsigned long long lo = 0ull, hi = 0xFFFFFFFFull;  // predicate(k): mass{key(p) > k} <= budget; true at hi, monotone in k
+        while (lo < hi) {                                  // (CTA-uniform: every thread sees the same block sums)
+            const unsigned mid = (unsigned)((lo + hi) >> 1);
             unsigned long long ma = 0ull;
-            for_kept([&](int, float z) { const float e = expf(z - mx); if (e / sum_pre > mid) ma += __float2ull_rn(e * SMP_FIX); });
+            for_kept([&](int, float z) { const float e = expf(z - mx); if (float_order_key(e / sum_pre) > mid) ma += __float2ull_rn(e * SMP_FIX); });
             ma = smp_block_sum64<THREADS>(ma, red_q);
-            if ((double)ma <= budget) hi = mid; else lo = mid;
+            if ((double)ma <= budget) hi = mid; else lo = (unsigned long long)mid + 1ull;
         }
-        p_lo = lo;
+        p_key = (unsigned)hi;
         unsigned long long m2 = 0ull;
-        for_kept([&](int, float z) { const float e = expf(z - mx); if (e / sum_pre > p_lo) m2 += __float2ull_rn(e * SMP_FIX); });
+        for_kept([&](int, float z) { const float e = expf(z - mx); if (float_order_key(e / sum_pre) >= p_key) m2 += __float2ull_rn(e * SMP_FIX); });
         m2 = smp_block_sum64<THREADS>(m2, red_q);
         sum = (float)m2 * (1.0f / SMP_FIX);                // soft-max over the surviving logits only
     }
@@ -375,7 +376,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
         float* po = a.probs_out + (size_t)b * V;
         for (int i4 = tid; i4 < V4; i4 += THREADS) reinterpret_cast<float4*>(po)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        for_kept([&](int i, float z) { const float e = expf(z - mx); if (e / sum_pre > p_lo) po[i] = e / sum; });
+        for_kept([&](int i, float z) { const float e = expf(z - mx); if (float_order_key(e / sum_pre) >= p_key) po[i] = e / sum; });
     }
     SMP_STAMP(3);
     // ---- draw: arg-max of p (greedy) or of p / q (exponential race); lowest index wins ties
@@ -383,7 +384,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, const int b, un
     const float* nz = a.noise ? a.noise + ((size_t)(a.noise_per_step ? step : 0) * a.B + b) * V : nullptr;
     for_kept([&](int i, float z) {
         const float e = expf(z - mx);
-        if (e / sum_pre > p_lo && e > 0.f) {
+        if (float_order_key(e / sum_pre) >= p_key && e > 0.f) {
             float sv = e / sum;
             if (a.sample_logits) sv = sv / (nz ? nz[i] : exp1_noise(a.seed_lo, a.seed_hi, i, b, step));
             if (sv > best || (sv == best && i < besti)) { best = sv; besti = i; }
