@@ -452,6 +452,17 @@ static int conv_fwd(cudaStream_t st, const ConvW& c, const Act& x, int ups, int 
 }
 static int gn_fwd(cudaStream_t st, const NormW& nw, const Act& x, bf16* y, int swish, float* stats) {
     const int G = 32;
+    const int C8 = x.C / 8;
+    if (x.C % 64 == 0 && 256 % C8 == 0 && x.H * x.W >= 4 * GN_CHUNKS && ((uintptr_t)x.p % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+        ((uintptr_t)nw.w % 16) == 0 && ((uintptr_t)nw.b % 16) == 0) {
+        // coalesced two-stage statistics + 16-byte apply (vision.cuh); `stats` has room for the partial sums behind the [B*32][2] block
+        float* part = stats + (size_t)x.B * G * 2;
+        CAR_LAUNCH(groupnorm_partial_kernel, dim3(GN_CHUNKS, x.B), 256, 0, st, (const bf16*)x.p, part, x.H * x.W, x.C);
+        CAR_LAUNCH(groupnorm_finish_kernel, x.B, 32, 0, st, (const float*)part, stats, x.H * x.W, x.C);
+        CAR_LAUNCH(groupnorm_apply8_kernel, gsz(x.n() / 8), 256, 0, st, (const bf16*)x.p, (const float*)stats, (const bf16*)nw.w, (const bf16*)nw.b, y, x.n() / 8,
+                   x.H * x.W, x.C, swish);
+        return CAR_OK;
+    }
     CAR_LAUNCH(groupnorm_stats_kernel, x.B * G, 512, 0, st, x.p, stats, x.H * x.W, x.C, G);
     CAR_LAUNCH(groupnorm_apply_kernel, gsz(x.n()), 256, 0, st, x.p, stats, nw.w, nw.b, y, x.n(), x.H * x.W, x.C, G, swish);
     return CAR_OK;
@@ -511,12 +522,12 @@ static int vq_scratch(cudaStream_t st, CarVQ* m, int B, int Hmax, int Wmax, int 
     const CarVQDesc& d = m->d;
     const size_t act = (size_t)B * Hmax * Wmax * Cfull * 2;            // largest activation (ch channels at full res)
     const int hw = h16 * w16, hwp = (hw + 31) & ~31, Cmax = d.ch * d.ch_mult[d.n_levels - 1];
-    size_t need = 5 * (act + 256) + (size_t)B * 32 * 2 * 4 + 256 + (size_t)B * hw * hwp * 6 + 512 + (size_t)B * Cmax * hwp * 2 + 256 + extra + 256;
+    size_t need = 5 * (act + 256) + (size_t)B * 32 * 2 * 4 * (1 + GN_CHUNKS) + 256 + (size_t)B * hw * hwp * 6 + 512 + (size_t)B * Cmax * hwp * 2 + 256 + extra + 256;
     CAR_TRY(m->ws.reserve(need));
     m->ws.reset();
     *bufA = (bf16*)m->ws.take(act); *bufB = (bf16*)m->ws.take(act);
     s.t0 = (bf16*)m->ws.take(act); s.t1 = (bf16*)m->ws.take(act); s.t2 = (bf16*)m->ws.take(act);
-    s.stats = (float*)m->ws.take((size_t)B * 32 * 2 * 4);
+    s.stats = (float*)m->ws.take((size_t)B * 32 * 2 * 4 * (1 + GN_CHUNKS));
     s.S = (float*)m->ws.take((size_t)B * hw * hwp * 4); s.P = (bf16*)m->ws.take((size_t)B * hw * hwp * 2);
     s.vT = (bf16*)m->ws.take((size_t)B * Cmax * hwp * 2);
     if (extra_p) *extra_p = m->ws.take(extra);
@@ -565,6 +576,11 @@ static int vq_decode_impl(CarVQ* m, const int32_t* codes, const float* quant, in
     }
     CAR_TRY(gn_fwd(st, m->d_norm_out, x, s.t0, 1, s.stats));
     Act y{s.t0, B, x.H, x.W, x.C};
+    if (m->d_conv_out.cout == 3 && m->d_conv_out.cin_pad == y.C && y.C % 8 == 0 && 27 * y.C * 2 <= 48 * 1024) {
+        CAR_LAUNCH(conv3x3_to3_kernel, gsz((long long)B * y.H * y.W), 256, (size_t)27 * y.C * 2, st, (const bf16*)y.p, (const bf16*)m->d_conv_out.w,
+                   (const bf16*)m->d_conv_out.b, out, B, y.H, y.W, y.C);
+        return CAR_OK;
+    }
     return conv_fwd(st, m->d_conv_out, y, 0, 0, nullptr, nullptr, x.H, x.W, out);
 }
 

@@ -87,6 +87,118 @@ __global__ void groupnorm_apply_kernel(const bf16* __restrict__ x, const float* 
     }
 }
 
+// ---- GroupNorm(32), coalesced two-stage form (r2).  The one-block-per-(image, group) kernel above reads 8-byte pieces at a stride of
+// C * 2 bytes (a quarter of every 32-byte sector) and wrote / read bf16 one element per thread: 19 ms per 8-image VQ decode.  Here
+// every block streams a contiguous run of pixels with 16-byte loads, a thread keeps sums for the (at most two) groups its fixed
+// 8-channel slot belongs to, partial sums are combined in a fixed order (deterministic), and a tiny second kernel folds the chunks.
+constexpr int GN_CHUNKS = 64;                 // partial-sum chunks per image
+__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const bf16* __restrict__ x, float* __restrict__ part /*[B][GN_CHUNKS][32][2]*/, int HW, int C) {
+    __shared__ float sh[256][4];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int C8 = C >> 3, cg = C >> 5;                      // 16-byte slots per pixel, channels per group (4, 8, 16, ...)
+    const int ppi = 256 / C8;                                // pixels per block iteration (C8 divides 256: C in {128, 256, 512})
+    const int slot = threadIdx.x % C8, prow = threadIdx.x / C8;
+    const long long p0 = (long long)HW * chunk / GN_CHUNKS, p1 = (long long)HW * (chunk + 1) / GN_CHUNKS;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;           // first / second half of the slot's 8 channels
+    const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
+    for (long long pix = p0 + prow; pix < p1; pix += ppi) {
+        const uint4 v = base[pix * C8 + slot];
+        float a, c;
+        unpack_bf16x2(v.x, a, c); s0 += a + c; q0 += a * a + c * c;
+        unpack_bf16x2(v.y, a, c); s0 += a + c; q0 += a * a + c * c;
+        unpack_bf16x2(v.z, a, c); s1 += a + c; q1 += a * a + c * c;
+        unpack_bf16x2(v.w, a, c); s1 += a + c; q1 += a * a + c * c;
+    }
+    sh[threadIdx.x][0] = s0; sh[threadIdx.x][1] = q0; sh[threadIdx.x][2] = s1; sh[threadIdx.x][3] = q1;
+    __syncthreads();
+    if (threadIdx.x < 32) {                                   // thread g folds the partials of group g in a fixed order
+        const int g = threadIdx.x;
+        float s = 0.f, q = 0.f;
+        for (int t = 0; t < 256; ++t) {
+            const int sl = t % C8;
+            const int c_lo = sl * 8, c_hi = sl * 8 + 4;       // first channels of the slot's two halves
+            if (c_lo / cg == g) { s += sh[t][0]; q += sh[t][1]; }
+            if (c_hi / cg == g) { s += sh[t][2]; q += sh[t][3]; }
+        }
+        float* o = part + (((size_t)b * GN_CHUNKS + chunk) * 32 + g) * 2;
+        o[0] = s; o[1] = q;
+    }
+}
+__global__ void groupnorm_finish_kernel(const float* __restrict__ part, float* __restrict__ stats /*[B*32][2]*/, int HW, int C) {
+    const int bg = blockIdx.x * blockDim.x + threadIdx.x;     // b * 32 + g
+    if (bg >= (int)gridDim.x * (int)blockDim.x) return;
+    const int b = bg >> 5, g = bg & 31;
+    float s = 0.f, q = 0.f;
+    for (int c = 0; c < GN_CHUNKS; ++c) { const float* p = part + (((size_t)b * GN_CHUNKS + c) * 32 + g) * 2; s += p[0]; q += p[1]; }
+    const float n = (float)HW * (float)(C >> 5);
+    const float mean = s / n;
+    stats[bg * 2] = mean;
+    stats[bg * 2 + 1] = rsqrtf(fmaxf(q / n - mean * mean, 0.f) + 1e-6f);
+}
+// y = GN(x) (* swish), 8 channels (16 bytes) per thread
+__global__ void groupnorm_apply8_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const bf16* __restrict__ w,
+                                        const bf16* __restrict__ bsh, bf16* __restrict__ y, long long total8, int HW, int C, int swish) {
+    const int C8 = C >> 3, cg = C >> 5;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int slot = (int)(i % C8);
+        const int b = (int)(i / ((long long)HW * C8));
+        const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+        const uint4 wv = reinterpret_cast<const uint4*>(w)[slot], bv = reinterpret_cast<const uint4*>(bsh)[slot];
+        const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {wv.x, wv.y, wv.z, wv.w}, bi[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t oi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = slot * 8 + 2 * k;
+            const float* st = stats + ((size_t)b * 32 + c / cg) * 2;       // (both channels of a pair lie in one group: cg is even)
+            float a0, a1, w0, w1, b0, b1;
+            unpack_bf16x2(vi[k], a0, a1); unpack_bf16x2(wi[k], w0, w1); unpack_bf16x2(bi[k], b0, b1);
+            float r0 = (a0 - st[0]) * st[1] * w0 + b0, r1 = (a1 - st[0]) * st[1] * w1 + b1;
+            if (swish) { r0 = r0 / (1.0f + expf(-r0)); r1 = r1 / (1.0f + expf(-r1)); }
+            __nv_bfloat162 o = __floats2bfloat162_rn(r0, r1);
+            oi[k] = *reinterpret_cast<uint32_t*>(&o);
+        }
+        reinterpret_cast<uint4*>(y)[i] = make_uint4(oi[0], oi[1], oi[2], oi[3]);
+    }
+}
+// last decoder convolution (conv_out, vq_model.py:193: 3x3, C -> 3 channels, fp32 NCHW image out).  An implicit GEMM would compute
+// a 128-wide tile for 3 output channels; here one thread owns one pixel: 9 taps x C channels by 16-byte loads, weights in shared memory.
+__global__ void __launch_bounds__(256) conv3x3_to3_kernel(const bf16* __restrict__ x /*NHWC*/, const bf16* __restrict__ w /*[3][9][C]*/,
+                                                           const bf16* __restrict__ bias, float* __restrict__ out /*[B][3][H][W]*/, int B, int H, int W, int C) {
+    extern __shared__ bf16 c3_w[];                             // [3][9][C]
+    for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) c3_w[i] = w[i];
+    __syncthreads();
+    const long long total = (long long)B * H * W;
+    const int C8 = C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        const long long r = i / W;
+        const int yy = (int)(r % H), b = (int)(r / H);
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int tap = 0; tap < 9; ++tap) {
+            const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+            if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+            const uint4* px = reinterpret_cast<const uint4*>(x + (((size_t)b * H + sy) * W + sx) * C);
+            for (int c8 = 0; c8 < C8; ++c8) {
+                const uint4 v = px[c8];
+                const uint32_t vi[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(c3_w + ((size_t)o * 9 + tap) * C + c8 * 8);
+                    const uint32_t wi[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float a0, a1, w0, w1;
+                        unpack_bf16x2(vi[k], a0, a1); unpack_bf16x2(wi[k], w0, w1);
+                        acc[o] = fmaf(a0, w0, acc[o]); acc[o] = fmaf(a1, w1, acc[o]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 3; ++o) out[(((size_t)b * 3 + o) * H + yy) * W + xx] = acc[o] + tof(bias[o]);
+    }
+}
+
 // ---- layout / dtype conversions
 template <typename TI>
 __global__ void nchw_to_nhwc_bf16_kernel(const TI* __restrict__ x, bf16* __restrict__ y, int B, int C, int HW, int Cpad) {
