@@ -226,6 +226,11 @@ static int dino_forward_t(CarDino* m, const TI* image, int B, int H, int W, void
             p.sB = (long long)Tn * C; p.sC = (long long)C * Tp; p.bias = (const bf16*)Ly.b_v; p.bias_along_m = 1;
             CAR_TRY(dense(st, p, B));
         }
+        static const bool fused_attn = [] { const char* e = getenv("CAR_VIT_FA"); return e ? atoi(e) != 0 : true; }();
+        if (fused_attn && C % 64 == 0 && ((uintptr_t)qk % 16) == 0 && ((uintptr_t)vT % 16) == 0) {
+            // fused attention (vision.cuh): scores / probabilities never leave the SM
+            CAR_LAUNCH(vit_attention_kernel, dim3((Tn + 63) / 64, heads, B), 128, 0, st, (const bf16*)qk, (const bf16*)vT, ctx, Tn, Tp, C, scale);
+        } else {
         // scores S[b,hd] = q k^T * 1/8  (fp32), soft-max -> P (bf16, zero padded), ctx = P V
         for (int hd = 0; hd < heads; ++hd) {
             DenseP p = dp_plain(qk + hd * 64, 2 * C, qk + C + hd * 64, 2 * C, Tn, Tn, 64, S + (size_t)hd * Tn * Tp, Tp);
@@ -237,6 +242,7 @@ static int dino_forward_t(CarDino* m, const TI* image, int B, int H, int W, void
             DenseP p = dp_plain(P + (size_t)hd * Tn * Tp, Tp, vT + (size_t)hd * 64 * Tp, Tp, Tn, 64, Tp, ctx + hd * 64, C);
             p.sA = (long long)heads * Tn * Tp; p.sB = (long long)C * Tp; p.sC = (long long)Tn * C;
             CAR_TRY(dense(st, p, B));
+        }
         }
         {   // x = x + ls1 * (dense(ctx) + b)
             DenseP p = dp_plain(ctx, C, (const bf16*)Ly.w_o, C, (int)rows, C, C, x, C);

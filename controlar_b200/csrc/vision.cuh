@@ -87,6 +87,119 @@ __global__ void groupnorm_apply_kernel(const bf16* __restrict__ x, const float* 
     }
 }
 
+// ---- fused multi-head attention of the control encoders (Dinov2SelfAttention / ViTSelfAttention, head dim 64): one CTA = 64
+// queries of one (image, head), 4 warps x 16 queries; key tiles of 64 stream through shared memory; S = q k^T * scale in fp32
+// (mma.sync m16n8k16), online soft-max in fp32, probabilities rounded to bf16, ctx += P V (fp32 accumulate), bf16 out.
+// Replaces the per-head S GEMM -> soft-max -> P V GEMM chain (fp32 S and bf16 P round trips through HBM: ~10 of DINOv2-small's 17 ms).
+//   qk  [B*Tn][2C]: q at column hd*64, k at column C + hd*64 (bias included)      vT [B][C][Tp]: V^T per image, row = channel
+//   ctx [B*Tn][C]
+constexpr int FA_PITCH = 72;                                  // bf16 per shared-memory row (64 + 8: conflict-free 4-byte fragment loads)
+__global__ void __launch_bounds__(128) vit_attention_kernel(const bf16* __restrict__ qk, const bf16* __restrict__ vT, bf16* __restrict__ ctx,
+                                                             int Tn, int Tp, int C, float scale) {
+    __shared__ __align__(16) bf16 sK[64 * FA_PITCH];          // [key][dim]
+    __shared__ __align__(16) bf16 sV[64 * FA_PITCH];          // [dim][key]
+    const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const size_t ldq = (size_t)2 * C;
+    // Q fragments of this warp's 16 rows (rows past Tn read row Tn - 1; their output is never stored)
+    const int r_lo = min(q0 + warp * 16 + g, Tn - 1), r_hi = min(q0 + warp * 16 + g + 8, Tn - 1);
+    const bf16* qlo = qk + ((size_t)b * Tn + r_lo) * ldq + hd * 64;
+    const bf16* qhi = qk + ((size_t)b * Tn + r_hi) * ldq + hd * 64;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 2 * t);
+        qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 2 * t);
+        qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 8 + 2 * t);
+        qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 8 + 2 * t);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+    const bf16* kbase = qk + (size_t)b * Tn * ldq + C + hd * 64;
+    const bf16* vbase = vT + ((size_t)b * C + hd * 64) * Tp;
+    for (int k0 = 0; k0 < Tn; k0 += 64) {
+        __syncthreads();                                       // previous tile consumed
+        for (int i = tid; i < 64 * 8; i += 128) {              // 64 rows x 8 chunks of 16 bytes, both tiles
+            const int r = i >> 3, c = i & 7;
+            const int key = min(k0 + r, Tn - 1);               // keys past Tn are masked below
+            *reinterpret_cast<uint4*>(sK + r * FA_PITCH + c * 8) = *reinterpret_cast<const uint4*>(kbase + (size_t)key * ldq + c * 8);
+            const int kc = k0 + c * 8;                         // vT rows are padded to Tp (>= Tn, multiple of 32) and zero past Tn
+            uint4 vv = make_uint4(0u, 0u, 0u, 0u);
+            if (kc < Tp) vv = *reinterpret_cast<const uint4*>(vbase + (size_t)r * Tp + kc);
+            *reinterpret_cast<uint4*>(sV + r * FA_PITCH + c * 8) = vv;
+        }
+        __syncthreads();
+        // S tile 16 x 64
+        float sacc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (j * 8 + g) * FA_PITCH + ks * 16 + 2 * t);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (j * 8 + g) * FA_PITCH + ks * 16 + 8 + 2 * t);
+                mma_bf16_16816(sacc[j], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+            }
+        }
+        // scale, mask the keys past Tn, running max
+        float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int key = k0 + j * 8 + 2 * t + (e & 1);
+                const float v = key < Tn ? sacc[j][e] * scale : -INFINITY;
+                sacc[j][e] = v;
+                if (e < 2) mx_lo = fmaxf(mx_lo, v); else mx_hi = fmaxf(mx_hi, v);
+            }
+        }
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        const float c_lo = __expf(m_lo - mx_lo), c_hi = __expf(m_hi - mx_hi);     // exp(-inf) = 0 on the first tile
+        m_lo = mx_lo; m_hi = mx_hi;
+        l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi; }
+        // probabilities -> bf16 A fragments (two adjacent 8-key blocks = one k16 step), row sums of the ROUNDED values
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = rnd<bf16>(__expf(sacc[j][0] - m_lo)), p1 = rnd<bf16>(__expf(sacc[j][1] - m_lo));
+            const float p2 = rnd<bf16>(__expf(sacc[j][2] - m_hi)), p3 = rnd<bf16>(__expf(sacc[j][3] - m_hi));
+            l_lo += p0 + p1; l_hi += p2 + p3;
+            __nv_bfloat162 lo2 = __floats2bfloat162_rn(p0, p1), hi2 = __floats2bfloat162_rn(p2, p3);
+            pa[j >> 1][(j & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo2);
+            pa[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi2);
+        }
+        // ctx += P V : B fragments from V^T [dim][key]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sV + (j * 8 + g) * FA_PITCH + ks * 16 + 2 * t);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sV + (j * 8 + g) * FA_PITCH + ks * 16 + 8 + 2 * t);
+                mma_bf16_16816(o[j], pa[ks][0], pa[ks][1], pa[ks][2], pa[ks][3], b0, b1);
+            }
+        }
+    }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const int row_lo = q0 + warp * 16 + g, row_hi = row_lo + 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (row_lo < Tn) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(o[j][0] / l_lo, o[j][1] / l_lo);
+            *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * Tn + row_lo) * C + hd * 64 + j * 8 + 2 * t) = v;
+        }
+        if (row_hi < Tn) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(o[j][2] / l_hi, o[j][3] / l_hi);
+            *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * Tn + row_hi) * C + hd * 64 + j * 8 + 2 * t) = v;
+        }
+    }
+}
+
 // ---- GroupNorm(32), coalesced two-stage form (r2).  The one-block-per-(image, group) kernel above reads 8-byte pieces at a stride of
 // C * 2 bytes (a quarter of every 32-byte sector) and wrote / read bf16 one element per thread: 19 ms per 8-image VQ decode.  Here
 // every block streams a contiguous run of pixels with 16-byte loads, a thread keeps sums for the (at most two) groups its fixed
