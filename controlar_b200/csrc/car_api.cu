@@ -553,7 +553,13 @@ static int enqueue_block_dense(CarState* s, int l, cudaStream_t st) {
     CAR_TRY(dense_linear(st, s->t1, dim, m->wqkv[l], rows, 3 * dim, dim, ACT_NONE, nullptr, 0, s->qkvP, 3 * dim));
     CAR_LAUNCH(rope_kv_write_kernel, sm_count() * 8, 256, 0, st, (const bf16*)s->qkvP, s->rope, (bf16*)s->qP, (bf16*)s->kc[l], (bf16*)s->vc[l], rows, s->T, dim,
                d.n_head, s->S);
-    CAR_TRY(launch_attn_prefill<bf16>(s, l, st));
+    static const bool fa = [] { const char* e = getenv("CAR_PREFILL_FA"); return e ? atoi(e) != 0 : true; }();
+    if (fa) {   // prefix attention on the tensor cores (attention.cuh): 64 query rows per CTA
+        CAR_LAUNCH(attn_prefill_mma_kernel, dim3((s->T + 63) / 64, d.n_head, s->b_eff), 128, 0, st, (const bf16*)s->qP, (const bf16*)s->kc[l],
+                   (const bf16*)s->vc[l], (const int*)s->emb_mask, s->T, d.n_head, s->S, s->T, s->T, (bf16*)s->attnP);
+    } else {
+        CAR_TRY(launch_attn_prefill<bf16>(s, l, st));
+    }
     CAR_TRY(dense_linear(st, s->attnP, dim, m->wo[l], rows, dim, dim, ACT_NONE, s->hP, dim, s->hP, dim));
     CAR_LAUNCH((rmsnorm_rows_kernel<bf16>), rows, 256, 0, st, (const bf16*)s->hP, (const bf16*)m->ffn_norm[l], (bf16*)s->t1, dim, d.norm_eps);
     CAR_TRY(dense_linear(st, s->t1, dim, m->w1[l], rows, F, dim, ACT_NONE, nullptr, 0, s->gP, F));
