@@ -1153,6 +1153,17 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
     return CAR_OK;
 }
 
+// fused AdamW step over a device-resident tensor table (train.cuh); bias corrections from the step count (1-based)
+extern "C" int car_adamw_step(const void* tensors_dev, const void* chunks_dev, int32_t n_chunks, float lr, float beta1, float beta2, float eps,
+                              int32_t step, void* stream) {
+    if (!tensors_dev || !chunks_dev) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (n_chunks <= 0 || step < 1) CAR_FAIL(CAR_ERR_ARG, "n_chunks must be positive and step 1-based");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    CAR_LAUNCH(adamw_multi_kernel, n_chunks, 256, 0, (cudaStream_t)stream, (const CarAdamWTensorDev*)tensors_dev, (const int2*)chunks_dev, lr, beta1, beta2,
+               eps, bc1, sqrtf(bc2));
+    return CAR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // T5 text encoder forward: language/t5.py:58-79 -> HF T5EncoderModel(...).last_hidden_state, bf16.
 // v1.1 / flan architecture: gated gelu_new feed-forward, no biases, RMS layer norm (eps 1e-6), relative position bias of block 0

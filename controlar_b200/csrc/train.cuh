@@ -204,3 +204,27 @@ __global__ void tr_ce_reduce_kernel(const float* __restrict__ nll, const float* 
         loss[0] = valid ? ta / fmaxf(tc, 1.f) : ta / (float)rows;
     }
 }
+
+// ---- fused multi-tensor AdamW (row f1: the optimiser step of autoregressive/train/train_c2i.py:28-50, torch.optim.AdamW(fused=True)) ----
+// One launch for every parameter of the model: chunk c of the chunk list covers up to ADAMW_CHUNK elements of tensor `t`.
+// Arithmetic = ATen's fused kernel in fp32: decoupled weight decay, exp_avg = lerp(exp_avg, grad, 1 - beta1),
+// exp_avg_sq = beta2 * exp_avg_sq + (1 - beta2) * grad^2, param -= (lr / bc1) * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps).
+struct CarAdamWTensorDev { float* p; const float* g; float* m; float* v; long long n; float weight_decay; int pad_; };
+constexpr int ADAMW_CHUNK = 65536;
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const CarAdamWTensorDev* __restrict__ tensors, const int2* __restrict__ chunks,
+                                                          float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+    const int2 ck = chunks[blockIdx.x];                        // {tensor index, chunk index inside the tensor}
+    const CarAdamWTensorDev T = tensors[ck.x];
+    const long long lo = (long long)ck.y * ADAMW_CHUNK, hi = min(T.n, lo + ADAMW_CHUNK);
+    const float step_size = lr / bc1, decay = lr * T.weight_decay;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float g = T.g[i];
+        float p = T.p[i], m = T.m[i], v = T.v[i];
+        if (T.weight_decay != 0.f) p -= decay * p;
+        m = m + (g - m) * (1.f - beta1);
+        v = beta2 * v + (1.f - beta2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p -= step_size * m / denom;
+        T.p[i] = p; T.m[i] = m; T.v[i] = v;
+    }
+}

@@ -276,6 +276,13 @@ int car_hed_create(const void* const* tensors, int32_t n_tensors, void* stream, 
 int car_hed_forward(CarHED* m, const float* img, int32_t B, int32_t H, int32_t W, float* edge_out, float* proj_out, void* stream);
 int car_hed_destroy(CarHED* m);
 
+/* Fused multi-tensor AdamW step (row f1: autoregressive/train/train_c2i.py:28-50 builds torch.optim.AdamW(fused=True)).
+ * tensors_dev: device array of { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel; float weight_decay;
+ * int32 pad } (48 bytes each); chunks_dev: device array of int32 pairs { tensor index, chunk index } — chunk = 65536 elements;
+ * step is 1-based (bias corrections 1 - beta^step).  fp32 state, ATen's fused arithmetic. */
+int car_adamw_step(const void* tensors_dev, const void* chunks_dev, int32_t n_chunks, float lr, float beta1, float beta2, float eps,
+                   int32_t step, void* stream);
+
 /* T5 text encoder: language/t5.py:58-79 — HF T5EncoderModel(input_ids, attention_mask).last_hidden_state in
  * bf16 (v1.1 / flan architecture: gated gelu_new feed-forward, no biases, RMS layer norm, relative position bias of block 0 shared
  * by all blocks, no 1/sqrt(d) scaling).  Weights ([out, in] row-major bf16, HF state-dict tensors) are borrowed until
