@@ -30,7 +30,7 @@ class CarWeights(C.Structure):
 
 class CarTrainWeights(C.Structure):
     _fields_ = [("w", CarWeights), ("adapter_fc1", C.c_void_p), ("adapter_fc2", C.c_void_p), ("cap_uncond", C.c_void_p),
-                ("adapter_dim", C.c_int32), ("num_classes", C.c_int32)]
+                ("adapter_dim", C.c_int32), ("num_classes", C.c_int32), ("cond_uncond", C.c_void_p)]
 
 
 class CarSampling(C.Structure):
@@ -68,6 +68,7 @@ PROTOTYPES = {
                                    C.POINTER(C.c_void_p)]),
     "car_train_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "car_train_backward": (C.c_int, [C.c_void_p, C.POINTER(CarTrainWeights), C.c_void_p, C.c_void_p, C.c_void_p]),
     "car_train_destroy": (C.c_int, [C.c_void_p]),
     "car_canny_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "car_canny_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

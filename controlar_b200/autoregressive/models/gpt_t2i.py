@@ -266,7 +266,7 @@ class Transformer(nn.Module):
     def forward(self, idx, cond_idx, input_pos=None, targets=None, mask=None, valid=None, condition=None,
                 control_strength=1):
         """Reference gpt_t2i.py:409-484.  Inference branches -> (logits fp32, None); with both ``idx`` and ``cond_idx`` the
-        teacher-forced training branch -> (logits fp32 [B, n+1, V], loss) — forward and loss only, no autograd graph yet."""
+        teacher-forced training branch -> (logits fp32 [B, n+1, V], loss); `loss.backward()` runs the library's backward."""
         if idx is not None and cond_idx is not None:
             return self._train_forward(idx, cond_idx, targets, mask, valid, condition)
         if self._car_state is None:
@@ -312,6 +312,12 @@ class Transformer(nn.Module):
         else:
             drop = torch.zeros(B, dtype=torch.bool, device=idx.device)
         feat = self.adapter(condition) if condition is not None else None      # control encoder (CUDA path of vision.py)
+        if targets is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # loss.backward() works like in the reference's train loop (train_c2i_canny.py:200-211): the library's own backward
+            # (car_train_backward) behind a torch.autograd.Function; gradients land in .grad of this module's parameters and, when
+            # `feat` is part of an autograd graph, flow on into the control encoder
+            names = _engine.ARTrainHandle.grad_params(self)
+            return _TrainStep.apply(self, th, idx, cond_idx, feat, drop, mask, targets, valid, *[p for _, p in names])
         return th.forward(idx, cond_idx, feat, drop, mask, targets, valid)
 
     def _n_img_check(self, condition):
@@ -321,6 +327,30 @@ class Transformer(nn.Module):
 
     def get_fsdp_wrap_module_list(self) -> List[nn.Module]:
         return list(self.layers)
+
+
+class _TrainStep(torch.autograd.Function):
+    """(logits, loss) = car_train_forward; backward = car_train_backward.  Only `loss` is differentiable (the logits come back
+    detached: the train scripts never differentiate through them)."""
+
+    @staticmethod
+    def forward(ctx, module, handle, idx, cond_idx, feat, drop, mask, targets, valid, *params):
+        logits, loss = handle.forward(idx, cond_idx, feat, drop, mask, targets, valid)
+        ctx.module, ctx.handle, ctx.generation = module, handle, handle.generation
+        ctx.want_feat = feat is not None and feat.requires_grad
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(logits)
+        return logits, loss.clone()
+
+    @staticmethod
+    def backward(ctx, _g_logits, g_loss):
+        if ctx.handle.generation != ctx.generation:
+            raise RuntimeError("controlar_b200: another training forward ran on this module since this loss was computed; the backward "
+                               "recomputes from the state of the LAST forward (call loss.backward() before the next forward)")
+        grads, dfeat = ctx.handle.backward(ctx.module, loss_grad=g_loss, want_feat_grad=ctx.want_feat)
+        names = _engine.ARTrainHandle.grad_params(ctx.module)
+        out = [grads.get(k) if p.requires_grad else None for k, p in names]
+        return (None, None, None, None, dfeat if ctx.want_feat else None, None, None, None, None, *out)
 
 
 def _factory(n_layer, n_head, dim):

@@ -14,6 +14,7 @@
 #include "gemm_dense.cuh"
 #include "gemm_tc5.cuh"
 #include "train.cuh"
+#include "train_bwd.cuh"
 #include "t5.cuh"
 #include <algorithm>
 
@@ -1009,6 +1010,18 @@ struct CarTrain {
     const float* rope;
     float *h, *nll;
     bf16 *x, *qkv, *q, *kc, *vc, *att, *g, *u, *act, *o, *cin, *ctmp, *ctok, *cadd, *lg;
+    // ---- backward (car_train_backward): the stream saved at every block input, gradient / transpose workspaces ----
+    float *hs, *dh, *h0, *scr, *part, *lse, *dsum;
+    bf16 *capx, *x2, *db, *dact, *dg, *du, *dx, *datt, *dq, *dk, *dv, *dqkv, *dlg, *wT, *yT, *xT, *dWb;
+    bf16 *m_t, *m_a, *m_da, *m_dt, *dctok, *dcin, *dadd;
+    size_t Rp_max;
+    // arguments of the last car_train_forward (borrowed until car_train_backward returns)
+    int fB = 0, fN = 0;
+    const int32_t *f_idx = nullptr, *f_targets = nullptr;
+    const void *f_cond = nullptr, *f_feat = nullptr;
+    const uint8_t *f_drop = nullptr, *f_mask = nullptr;
+    const float* f_valid = nullptr;
+    bool fwd_ok = false;
     std::vector<void*> owned;
 };
 
@@ -1061,6 +1074,24 @@ extern "C" int car_train_create(const CarModelDesc* desc, const CarTrainWeights*
     A(&t->g, R * F); A(&t->u, R * F); A(&t->act, R * F); A(&t->o, R * dim);
     A(&t->cin, RC * dim); A(&t->ctmp, std::max(RC, (size_t)t->maxB * d.cls_token_num) * dim); A(&t->ctok, RC * dim); A(&t->cadd, RC * dim);
     A(&t->lg, RC * V);
+    // backward workspaces
+    {
+        auto AF = [&](float** p, size_t elems) { if (rc == CAR_OK) rc = alloc_dev(t->owned, (void**)p, elems * 4); };
+        const size_t cap = (size_t)(d.model_type == 1 ? d.caption_dim : 8), ad = (size_t)w->adapter_dim;
+        const size_t rows_mlp = std::max(RC, (size_t)t->maxB * d.cls_token_num);
+        const size_t Rp = (std::max(R, rows_mlp) + 63) / 64 * 64;
+        const size_t maxN = std::max({(size_t)3 * dim, (size_t)F, (size_t)V}), maxK = std::max({(size_t)F, (size_t)dim, cap, ad});
+        const size_t maxW = std::max({(size_t)3 * dim * dim, (size_t)F * dim, (size_t)V * dim, (size_t)dim * cap, (size_t)dim * ad});
+        t->Rp_max = Rp;
+        AF(&t->hs, (size_t)L * R * dim); AF(&t->dh, R * dim); AF(&t->h0, R * dim); AF(&t->scr, R * dim);
+        AF(&t->part, (size_t)TR_COLSUM_CHUNKS * dim); AF(&t->lse, (size_t)t->maxB * d.n_head * t->maxS); AF(&t->dsum, (size_t)t->maxB * d.n_head * t->maxS);
+        A(&t->capx, (size_t)t->maxB * d.cls_token_num * cap);
+        A(&t->x2, R * dim); A(&t->db, R * dim); A(&t->dact, R * F); A(&t->dg, R * F); A(&t->du, R * F); A(&t->dx, R * dim);
+        A(&t->datt, R * dim); A(&t->dq, R * dim); A(&t->dk, R * dim); A(&t->dv, R * dim); A(&t->dqkv, R * 3 * dim); A(&t->dlg, RC * V);
+        A(&t->wT, maxW); A(&t->dWb, maxW); A(&t->yT, maxN * Rp); A(&t->xT, maxK * Rp);
+        A(&t->m_t, rows_mlp * dim); A(&t->m_a, rows_mlp * dim); A(&t->m_da, rows_mlp * dim); A(&t->m_dt, rows_mlp * dim);
+        A(&t->dctok, RC * dim); A(&t->dcin, RC * dim); A(&t->dadd, rows_mlp * dim);
+    }
     if (rc != CAR_OK) { for (void* p : t->owned) cudaFree(p); delete t; return rc; }
     *out = t;
     return CAR_OK;
@@ -1073,6 +1104,51 @@ extern "C" int car_train_destroy(CarTrain* t) {
     return CAR_OK;
 }
 
+static int tr_attn_smem(int S, size_t floats_per_warp, const void* fn, bool* attr_set, size_t* bytes) {
+    *bytes = (size_t)TRA_WARPS * floats_per_warp * 4;
+    (void)S;
+    if (*bytes > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "sequence too long for the plain attention kernels");
+    if (*bytes > 48 * 1024 && !*attr_set) {
+        CAR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        *attr_set = true;
+    }
+    return CAR_OK;
+}
+
+// One TransformerBlock (gpt_t2i.py:303-307) on the fp32 stream t->h, preceded by the control add of gpt_t2i.py:458-460 when the
+// block opens a third of the stack.  for_bwd: the recompute of car_train_backward — keeps the block input (after the control
+// add) in t->h0, the attention-side norm output in t->x, the feed-forward-side one in t->x2, and stops before w2 (t->h then
+// holds the stream between the two halves).
+static int tr_block_fwd(CarTrain* t, cudaStream_t st, int l, int B, int n_img, const uint8_t* mask, bool has_feat, bool for_bwd) {
+    const CarModelDesc& d = t->d;
+    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, T = d.cls_token_num, H = d.n_head;
+    const int n = n_img - 1, S = T + n, R = B * S, RC = B * n_img, step3 = L / 3;
+    if (has_feat && l % step3 == 0) {
+        CAR_TRY(tr_mlp(st, t->ctok, RC, dim, t->b_ctl1[l / step3], t->b_ctl2[l / step3], dim, t->ctmp, t->cadd));
+        CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->h, (const bf16*)t->cadd, B, n_img, S, T - 1, dim);
+    }
+    if (for_bwd) CAR_CUDA(cudaMemcpyAsync(t->h0, t->h, (size_t)R * dim * 4, cudaMemcpyDeviceToDevice, st));
+    static bool attr_set = false;
+    size_t att_smem = 0;
+    CAR_TRY(tr_attn_smem(S, (size_t)S, (const void*)tr_attention_kernel, &attr_set, &att_smem));
+    CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->attention_norm[l], t->x, dim, d.norm_eps, S, S, 0);
+    CAR_TRY(dense_linear(st, t->x, dim, t->b_wqkv[l], R, 3 * dim, dim, ACT_NONE, nullptr, 0, t->qkv, 3 * dim));
+    CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)t->qkv, t->rope, t->q, t->kc, t->vc, R, S, dim, H, S);
+    CAR_LAUNCH(tr_attention_kernel, (unsigned)(((long long)B * H * S + TRA_WARPS - 1) / TRA_WARPS), TRA_WARPS * 32, att_smem, st, (const bf16*)t->q,
+               (const bf16*)t->kc, (const bf16*)t->vc, mask, B, H, S, t->att);
+    CAR_TRY(dense_linear(st, t->att, dim, t->b_wo[l], R, dim, dim, ACT_NONE, nullptr, 0, t->o, dim));
+    CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
+    bf16* xn = for_bwd ? t->x2 : t->x;
+    CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->ffn_norm[l], xn, dim, d.norm_eps, S, S, 0);
+    CAR_TRY(dense_linear(st, xn, dim, t->b_w1[l], R, F, dim, ACT_NONE, nullptr, 0, t->g, F));
+    CAR_TRY(dense_linear(st, xn, dim, t->b_w3[l], R, F, dim, ACT_NONE, nullptr, 0, t->u, F));
+    CAR_LAUNCH(swiglu_kernel, 148 * 8, 256, 0, st, (const bf16*)t->g, (const bf16*)t->u, t->act, (long long)R * F);
+    if (for_bwd) return CAR_OK;
+    CAR_TRY(dense_linear(st, t->act, F, t->b_w2[l], R, dim, F, ACT_NONE, nullptr, 0, t->o, dim));
+    CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
+    return CAR_OK;
+}
+
 extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const int32_t* idx, const void* cond, const void* feat,
                                  const uint8_t* drop_ids, const uint8_t* mask, const int32_t* targets, const float* valid,
                                  float* logits_out, float* loss_out, void* stream) {
@@ -1081,9 +1157,10 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
     if ((loss_out != nullptr) != (targets != nullptr)) CAR_FAIL(CAR_ERR_ARG, "loss_out and targets go together");
     cudaStream_t st = (cudaStream_t)stream;
     const CarModelDesc& d = t->d;
-    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, V = d.vocab_size, T = d.cls_token_num, H = d.n_head;
+    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, V = d.vocab_size, T = d.cls_token_num;
     const int n = n_img - 1, S = T + n, R = B * S, RC = B * n_img;
     if (S > T + d.block_size) CAR_FAIL(CAR_ERR_ARG, "sequence longer than the RoPE table");
+    t->fwd_ok = false;
     // 0. autocast: bf16 copies of every nn.Linear weight, re-cast each forward (the fp32 masters may have been stepped)
     for (int l = 0; l < L; ++l) {
         CAR_TRY(tr_cast(st, t->wqkv[l], t->b_wqkv[l], (long long)3 * dim * dim)); CAR_TRY(tr_cast(st, t->wo[l], t->b_wo[l], (long long)dim * dim));
@@ -1100,8 +1177,8 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
     // 1. prefix rows: CaptionEmbedder (token_drop, cap_proj) gpt_t2i.py:145-162 or LabelEmbedder :78-97; image-token rows :423
     if (d.model_type == 1) {
         CAR_LAUNCH(tr_caption_select_kernel, tr_grid((long long)B * T * d.caption_dim), 256, 0, st, (const float*)cond, (const float*)t->w.cap_uncond,
-                   drop_ids, t->x, B, T, d.caption_dim);
-        CAR_TRY(tr_mlp(st, t->x, B * T, d.caption_dim, t->b_cap1, t->b_cap2, dim, t->ctmp, t->o));
+                   drop_ids, t->capx, B, T, d.caption_dim);
+        CAR_TRY(tr_mlp(st, t->capx, B * T, d.caption_dim, t->b_cap1, t->b_cap2, dim, t->ctmp, t->o));
         CAR_LAUNCH(tr_put_rows_bf16_kernel, tr_grid((long long)B * T * dim), 256, 0, st, (const bf16*)t->o, t->h, B, T, S, 0, dim);
     } else {
         CAR_LAUNCH(tr_embed_rows_kernel, B, 256, 0, st, (const float*)t->w.w.label_table, (const int*)cond, 1, drop_ids, t->w.num_classes, t->h, B, 1, S, 0, dim);
@@ -1110,36 +1187,13 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
     // 2. control tokens: adapter_mlp -> token_drop -> condition_mlp  gpt_t2i.py:424-427 (feat = the control encoder's output tokens)
     if (feat) {
         CAR_TRY(tr_mlp(st, (const bf16*)feat, RC, t->w.adapter_dim, t->b_ad1, t->b_ad2, dim, t->ctmp, t->cin));
-        CAR_LAUNCH(tr_zero_dropped_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->cin, drop_ids, B, (long long)n_img * dim);
+        CAR_LAUNCH(tr_select_uncond_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->cin, (const float*)t->w.cond_uncond, drop_ids, B, (long long)n_img * dim);
         CAR_TRY(tr_mlp(st, t->cin, RC, dim, t->b_cond1, t->b_cond2, dim, t->ctmp, t->ctok));
     }
-    // 3. blocks  gpt_t2i.py:456-468, TransformerBlock :303-307
-    const int step3 = L / 3;
-    static bool attr_set = false;
-    const size_t att_smem = (size_t)TRA_WARPS * S * 4;
-    if (att_smem > 48 * 1024 && !attr_set) {
-        CAR_CUDA(cudaFuncSetAttribute(tr_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    if (att_smem > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "sequence too long for the plain attention kernel");
+    // 3. blocks  gpt_t2i.py:456-468; the stream at every block input is kept for the backward's recompute
     for (int l = 0; l < L; ++l) {
-        if (feat && l % step3 == 0) {
-            CAR_TRY(tr_mlp(st, t->ctok, RC, dim, t->b_ctl1[l / step3], t->b_ctl2[l / step3], dim, t->ctmp, t->cadd));
-            CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->h, (const bf16*)t->cadd, B, n_img, S, T - 1, dim);
-        }
-        CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->attention_norm[l], t->x, dim, d.norm_eps, S, S, 0);
-        CAR_TRY(dense_linear(st, t->x, dim, t->b_wqkv[l], R, 3 * dim, dim, ACT_NONE, nullptr, 0, t->qkv, 3 * dim));
-        CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)t->qkv, t->rope, t->q, t->kc, t->vc, R, S, dim, H, S);
-        CAR_LAUNCH(tr_attention_kernel, (unsigned)(((long long)B * H * S + TRA_WARPS - 1) / TRA_WARPS), TRA_WARPS * 32, att_smem, st, (const bf16*)t->q,
-                   (const bf16*)t->kc, (const bf16*)t->vc, mask, B, H, S, t->att);
-        CAR_TRY(dense_linear(st, t->att, dim, t->b_wo[l], R, dim, dim, ACT_NONE, nullptr, 0, t->o, dim));
-        CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
-        CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->ffn_norm[l], t->x, dim, d.norm_eps, S, S, 0);
-        CAR_TRY(dense_linear(st, t->x, dim, t->b_w1[l], R, F, dim, ACT_NONE, nullptr, 0, t->g, F));
-        CAR_TRY(dense_linear(st, t->x, dim, t->b_w3[l], R, F, dim, ACT_NONE, nullptr, 0, t->u, F));
-        CAR_LAUNCH(swiglu_kernel, 148 * 8, 256, 0, st, (const bf16*)t->g, (const bf16*)t->u, t->act, (long long)R * F);
-        CAR_TRY(dense_linear(st, t->act, F, t->b_w2[l], R, dim, F, ACT_NONE, nullptr, 0, t->o, dim));
-        CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)R * dim), 256, 0, st, t->h, (const bf16*)t->o, B, S, S, 0, dim);
+        CAR_CUDA(cudaMemcpyAsync(t->hs + (size_t)l * R * dim, t->h, (size_t)R * dim * 4, cudaMemcpyDeviceToDevice, st));
+        CAR_TRY(tr_block_fwd(t, st, l, B, n_img, mask, feat != nullptr, false));
     }
     // 4. head on rows T-1 .. S-1 of every sample (gpt_t2i.py:469-473), loss :474-481
     CAR_LAUNCH(tr_rmsnorm_kernel, RC, 256, 0, st, (const float*)t->h, (const float*)t->w.w.norm, t->x, dim, d.norm_eps, n_img, S, T - 1);
@@ -1149,6 +1203,135 @@ extern "C" int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const in
         CAR_LAUNCH(tr_ce_reduce_kernel, 1, 1024, 0, st, (const float*)t->nll, valid, B, n_img, loss_out);
     } else if (logits_out) {
         CAR_LAUNCH(tr_put_rows_bf16_kernel, tr_grid((long long)RC * V), 256, 0, st, (const bf16*)t->lg, logits_out, 1, RC, RC, 0, V);
+    }
+    t->fB = B; t->fN = n_img; t->f_idx = idx; t->f_cond = cond; t->f_feat = feat; t->f_drop = drop_ids; t->f_mask = mask; t->f_targets = targets;
+    t->f_valid = valid;
+    t->fwd_ok = targets != nullptr;
+    return CAR_OK;
+}
+
+// ---- backward helpers: the two GEMMs of a linear layer's backward on the [N][K] x [M][K]^T tensor-core kernels ----------------
+// dX [rows][K] = bf16(dY [rows][N] . W [N][K] (+ resid)): needs W^T as the K-major operand
+static int tr_dgrad(CarTrain* t, cudaStream_t st, const bf16* dY, const bf16* Wb, int rows, int N, int K, const bf16* resid, bf16* dX) {
+    CAR_LAUNCH(tr_transpose_pad_kernel, dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st, Wb, t->wT, N, K, N);
+    return dense_linear(st, dY, N, t->wT, rows, K, N, ACT_NONE, resid, K, dX, K);
+}
+// grad [N][K] fp32 = float(bf16(dY^T . X)), dY [rows][N], X [rows][K]: both operands transposed, the row extent zero-padded to 64
+static int tr_wgrad(CarTrain* t, cudaStream_t st, const bf16* dY, const bf16* X, int rows, int N, int K, float* grad) {
+    if (!grad) return CAR_OK;
+    const int Rp = (rows + 63) / 64 * 64;
+    if ((size_t)Rp > t->Rp_max) CAR_FAIL(CAR_ERR_ARG, "row count beyond the transpose workspace");
+    CAR_LAUNCH(tr_transpose_pad_kernel, dim3(Rp / 32, (N + 31) / 32), dim3(32, 8), 0, st, dY, t->yT, rows, N, Rp);
+    CAR_LAUNCH(tr_transpose_pad_kernel, dim3(Rp / 32, (K + 31) / 32), dim3(32, 8), 0, st, X, t->xT, rows, K, Rp);
+    CAR_TRY(dense_linear(st, t->yT, Rp, t->xT, N, K, Rp, ACT_NONE, nullptr, 0, t->dWb, K));
+    CAR_LAUNCH(tr_bf16_to_f32_kernel, tr_grid((long long)N * K), 256, 0, st, (const bf16*)t->dWb, grad, (long long)N * K);
+    return CAR_OK;
+}
+// RMSNorm backward on `rows` output rows (row map like tr_rmsnorm_kernel) + the weight gradient
+static int tr_norm_bwd(CarTrain* t, cudaStream_t st, const float* h, const void* w, const bf16* dy, int rows, int nrows, int S, int row0, float* gw) {
+    const int dim = t->d.dim;
+    CAR_LAUNCH(tr_rmsnorm_bwd_kernel, rows, 256, 0, st, h, (const float*)w, dy, t->dh, t->scr, dim, t->d.norm_eps, nrows, S, row0);
+    if (gw) {
+        CAR_LAUNCH(tr_colsum_part_kernel, dim3((dim + 31) / 32, TR_COLSUM_CHUNKS), dim3(32, 8), 0, st, (const float*)t->scr, t->part, rows, dim);
+        CAR_LAUNCH(tr_colsum_final_kernel, (dim + 255) / 256, 256, 0, st, (const float*)t->part, gw, dim);
+    }
+    return CAR_OK;
+}
+// MLP backward (gpt_t2i.py:177-181: fc2(gelu_tanh(fc1 x)), no bias), recomputing the two intermediates.  dX (optional) = bf16(dT . fc1 (+ resid))
+static int tr_mlp_bwd(CarTrain* t, cudaStream_t st, const bf16* x, int rows, int K, const bf16* fc1, const bf16* fc2, const bf16* dY,
+                      const bf16* resid, bf16* dX, float* g1, float* g2) {
+    const int dim = t->d.dim;
+    CAR_TRY(dense_linear(st, x, K, fc1, rows, dim, K, ACT_NONE, nullptr, 0, t->m_t, dim));
+    CAR_LAUNCH(tr_gelu_kernel, tr_grid((long long)rows * dim), 256, 0, st, (const bf16*)t->m_t, t->m_a, (long long)rows * dim);
+    CAR_TRY(tr_wgrad(t, st, dY, t->m_a, rows, dim, dim, g2));
+    CAR_TRY(tr_dgrad(t, st, dY, fc2, rows, dim, dim, nullptr, t->m_da));
+    CAR_LAUNCH(tr_gelu_bwd_kernel, tr_grid((long long)rows * dim), 256, 0, st, (const bf16*)t->m_t, (const bf16*)t->m_da, t->m_dt, (long long)rows * dim);
+    CAR_TRY(tr_wgrad(t, st, t->m_dt, x, rows, dim, K, g1));
+    if (dX) CAR_TRY(tr_dgrad(t, st, t->m_dt, fc1, rows, dim, K, resid, dX));
+    return CAR_OK;
+}
+
+// Backward of the last car_train_forward(targets != NULL) on this handle: writes d loss / d parameter (fp32, OVERWRITTEN, scaled
+// by *loss_grad when given) through the non-NULL pointers of `g` (a CarTrainWeights whose fields point at gradient buffers of the
+// parameters' shapes) and d loss / d feat (bf16 [B, n_img, adapter_dim]) when d_feat is given.
+extern "C" int car_train_backward(CarTrain* t, const CarTrainWeights* g, void* d_feat, const float* loss_grad, void* stream) {
+    if (!t || !g) CAR_FAIL(CAR_ERR_ARG, "null argument");
+    if (!t->fwd_ok) CAR_FAIL(CAR_ERR_ARG, "car_train_backward needs a preceding car_train_forward with targets on the same handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CarModelDesc& d = t->d;
+    const int L = d.n_layer, dim = d.dim, F = d.ffn_dim, V = d.vocab_size, T = d.cls_token_num, H = d.n_head;
+    if (dim % 64 != 0 || F % 64 != 0 || V % 64 != 0) CAR_FAIL(CAR_ERR_UNSUPPORTED, "backward: dim, ffn_dim and vocab_size must be multiples of 64");
+    const int B = t->fB, n_img = t->fN, n = n_img - 1, S = T + n, R = B * S, RC = B * n_img, step3 = L / 3;
+    const bool has_feat = t->f_feat != nullptr;
+    const uint8_t* mask = t->f_mask;
+    static bool attr_q = false, attr_kv = false;
+    size_t smem_q = 0, smem_kv = 0;
+    CAR_TRY(tr_attn_smem(S, (size_t)2 * S + 128, (const void*)tr_attn_bwd_q_kernel, &attr_q, &smem_q));
+    CAR_TRY(tr_attn_smem(S, (size_t)2 * S + 128, (const void*)tr_attn_bwd_kv_kernel, &attr_kv, &smem_kv));
+    const unsigned att_grid = (unsigned)(((long long)B * H * S + TRA_WARPS - 1) / TRA_WARPS);
+    t->fwd_ok = false;                                         // the recompute below overwrites the forward's buffers
+    // ---- head: loss -> logits -> output projection -> final norm (gpt_t2i.py:469-481) ----
+    CAR_LAUNCH(tr_rmsnorm_kernel, RC, 256, 0, st, (const float*)t->h, (const float*)t->w.w.norm, t->x, dim, d.norm_eps, n_img, S, T - 1);
+    CAR_LAUNCH(tr_ce_grad_kernel, RC, 256, 0, st, (const bf16*)t->lg, (const int*)t->f_targets, t->f_valid, loss_grad, B, n_img, t->dlg, V);
+    CAR_TRY(tr_wgrad(t, st, t->dlg, t->x, RC, V, dim, (float*)g->w.output));
+    CAR_TRY(tr_dgrad(t, st, t->dlg, t->b_out, RC, V, dim, nullptr, t->dx));
+    CAR_CUDA(cudaMemsetAsync(t->dh, 0, (size_t)R * dim * 4, st));
+    CAR_TRY(tr_norm_bwd(t, st, t->h, t->w.w.norm, t->dx, RC, n_img, S, T - 1, (float*)g->w.norm));
+    // ---- blocks, last to first: recompute from the saved input stream, then feed-forward half, attention half, control add ----
+    bool first_ctl = true;
+    for (int l = L - 1; l >= 0; --l) {
+        CAR_CUDA(cudaMemcpyAsync(t->h, t->hs + (size_t)l * R * dim, (size_t)R * dim * 4, cudaMemcpyDeviceToDevice, st));
+        CAR_TRY(tr_block_fwd(t, st, l, B, n_img, mask, has_feat, true));
+        // feed-forward: h_out = h_mid + w2(silu(w1 x2) * w3 x2)
+        CAR_LAUNCH(tr_take_rows_bf16_kernel, tr_grid((long long)R * dim), 256, 0, st, (const float*)t->dh, t->db, B, S, S, 0, dim);
+        CAR_TRY(tr_wgrad(t, st, t->db, t->act, R, dim, F, g->w.w2 ? (float*)g->w.w2[l] : nullptr));
+        CAR_TRY(tr_dgrad(t, st, t->db, t->b_w2[l], R, dim, F, nullptr, t->dact));
+        CAR_LAUNCH(tr_swiglu_bwd_kernel, 148 * 8, 256, 0, st, (const bf16*)t->g, (const bf16*)t->u, (const bf16*)t->dact, t->dg, t->du, (long long)R * F);
+        CAR_TRY(tr_wgrad(t, st, t->dg, t->x2, R, F, dim, g->w.w1 ? (float*)g->w.w1[l] : nullptr));
+        CAR_TRY(tr_wgrad(t, st, t->du, t->x2, R, F, dim, g->w.w3 ? (float*)g->w.w3[l] : nullptr));
+        CAR_TRY(tr_dgrad(t, st, t->dg, t->b_w1[l], R, F, dim, nullptr, t->dx));
+        CAR_TRY(tr_dgrad(t, st, t->du, t->b_w3[l], R, F, dim, t->dx, t->dx));
+        CAR_TRY(tr_norm_bwd(t, st, t->h, t->ffn_norm[l], t->dx, R, S, S, 0, g->w.ffn_norm ? (float*)g->w.ffn_norm[l] : nullptr));
+        // attention: h_mid = h0 + wo(sdpa(rope(wqkv x1)))
+        CAR_LAUNCH(tr_take_rows_bf16_kernel, tr_grid((long long)R * dim), 256, 0, st, (const float*)t->dh, t->db, B, S, S, 0, dim);
+        CAR_TRY(tr_wgrad(t, st, t->db, t->att, R, dim, dim, g->w.wo ? (float*)g->w.wo[l] : nullptr));
+        CAR_TRY(tr_dgrad(t, st, t->db, t->b_wo[l], R, dim, dim, nullptr, t->datt));
+        CAR_LAUNCH(tr_attn_bwd_q_kernel, att_grid, TRA_WARPS * 32, smem_q, st, (const bf16*)t->q, (const bf16*)t->kc, (const bf16*)t->vc, mask,
+                   (const bf16*)t->datt, B, H, S, t->lse, t->dsum, t->dq);
+        CAR_LAUNCH(tr_attn_bwd_kv_kernel, att_grid, TRA_WARPS * 32, smem_kv, st, (const bf16*)t->q, (const bf16*)t->kc, (const bf16*)t->vc, mask,
+                   (const bf16*)t->datt, (const float*)t->lse, (const float*)t->dsum, B, H, S, t->dk, t->dv);
+        CAR_LAUNCH(tr_rope_bwd_kernel, 148 * 8, 256, 0, st, (const bf16*)t->dq, (const bf16*)t->dk, (const bf16*)t->dv, t->rope, t->dqkv, R, S, dim, H, S);
+        CAR_TRY(tr_wgrad(t, st, t->dqkv, t->x, R, 3 * dim, dim, g->w.wqkv ? (float*)g->w.wqkv[l] : nullptr));
+        CAR_TRY(tr_dgrad(t, st, t->dqkv, t->b_wqkv[l], R, 3 * dim, dim, nullptr, t->dx));
+        CAR_TRY(tr_norm_bwd(t, st, t->h0, t->attention_norm[l], t->dx, R, S, S, 0, g->w.attention_norm ? (float*)g->w.attention_norm[l] : nullptr));
+        // control add h[:, T-1:] += condition_layers[j](condition_token)
+        if (has_feat && l % step3 == 0) {
+            const int j = l / step3;
+            CAR_LAUNCH(tr_take_rows_bf16_kernel, tr_grid((long long)RC * dim), 256, 0, st, (const float*)t->dh, t->dadd, B, n_img, S, T - 1, dim);
+            CAR_TRY(tr_mlp_bwd(t, st, t->ctok, RC, dim, t->b_ctl1[j], t->b_ctl2[j], t->dadd, first_ctl ? nullptr : t->dctok, t->dctok,
+                               (float*)g->w.ctl_fc1[j], (float*)g->w.ctl_fc2[j]));
+            first_ctl = false;
+        }
+    }
+    // ---- embeddings and the prefix / control front ends ----
+    if (g->w.tok_embeddings) {
+        CAR_CUDA(cudaMemsetAsync((void*)g->w.tok_embeddings, 0, (size_t)V * dim * 4, st));
+        CAR_LAUNCH(tr_embed_grad_kernel, B * n, 256, 0, st, (const float*)t->dh, (const int*)t->f_idx, n, (const unsigned char*)nullptr, 0,
+                   (float*)g->w.tok_embeddings, B, n, S, T, dim);
+    }
+    if (d.model_type == 1) {
+        CAR_LAUNCH(tr_take_rows_bf16_kernel, tr_grid((long long)B * T * dim), 256, 0, st, (const float*)t->dh, t->dadd, B, T, S, 0, dim);
+        CAR_TRY(tr_mlp_bwd(t, st, t->capx, B * T, d.caption_dim, t->b_cap1, t->b_cap2, t->dadd, nullptr, nullptr, (float*)g->w.cap_fc1, (float*)g->w.cap_fc2));
+    } else if (g->w.label_table) {
+        CAR_CUDA(cudaMemsetAsync((void*)g->w.label_table, 0, (size_t)(t->w.num_classes + 1) * dim * 4, st));
+        CAR_LAUNCH(tr_embed_grad_kernel, B, 256, 0, st, (const float*)t->dh, (const int*)t->f_cond, 1, t->f_drop, t->w.num_classes, (float*)g->w.label_table,
+                   B, 1, S, 0, dim);
+    }
+    if (has_feat) {
+        CAR_TRY(tr_mlp_bwd(t, st, t->cin, RC, dim, t->b_cond1, t->b_cond2, t->dctok, nullptr, t->dcin, (float*)g->w.cond_fc1, (float*)g->w.cond_fc2));
+        CAR_LAUNCH(tr_zero_dropped_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->dcin, t->f_drop, B, (long long)n_img * dim);
+        CAR_TRY(tr_mlp_bwd(t, st, (const bf16*)t->f_feat, RC, t->w.adapter_dim, t->b_ad1, t->b_ad2, t->dcin, nullptr, (bf16*)d_feat,
+                           (float*)g->adapter_fc1, (float*)g->adapter_fc2));
     }
     return CAR_OK;
 }

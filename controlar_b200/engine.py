@@ -168,6 +168,9 @@ class ARTrainHandle:
             unc = m.cls_embedding.uncond_embedding.detach().to(torch.float32).contiguous()
             keep.append(unc)
             tw.cap_uncond = _ptr(unc)
+        cunc = m.condition_mlp.uncond_embedding.detach().to(torch.float32).contiguous()   # buffer, zeros unless a state dict says otherwise
+        keep.append(cunc)
+        tw.cond_uncond = _ptr(cunc)
         d = CarModelDesc(dtype=_lib.CAR_F32, dim=cfg.dim, n_layer=cfg.n_layer, n_head=cfg.n_head,
                          ffn_dim=m.layers[0].feed_forward.w1.weight.shape[0], vocab_size=cfg.vocab_size,
                          cls_token_num=cfg.cls_token_num, block_size=cfg.block_size,
@@ -203,7 +206,77 @@ class ARTrainHandle:
                                          None if m8 is None else _ptr(m8), None if tg is None else _ptr(tg),
                                          None if vf is None else _ptr(vf), _ptr(logits), None if loss is None else _ptr(loss), cur_stream()),
               "car_train_forward")
+        self._last = (idx, cond, feat, drop, m8, tg, vf)      # car_train_backward reads them again
+        self.generation = getattr(self, "generation", 0) + 1  # a backward belongs to the forward that produced its loss
         return logits, (None if loss is None else loss[0])
+
+    # ---- backward ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def grad_params(m):
+        """The parameters `car_train_backward` produces gradients for, in a fixed order (name, parameter)."""
+        out = [("tok_embeddings.weight", m.tok_embeddings.weight), ("norm.weight", m.norm.weight), ("output.weight", m.output.weight)]
+        for i, b in enumerate(m.layers):
+            pre = f"layers.{i}."
+            out += [(pre + "attention_norm.weight", b.attention_norm.weight), (pre + "attention.wqkv.weight", b.attention.wqkv.weight),
+                    (pre + "attention.wo.weight", b.attention.wo.weight), (pre + "ffn_norm.weight", b.ffn_norm.weight),
+                    (pre + "feed_forward.w1.weight", b.feed_forward.w1.weight), (pre + "feed_forward.w3.weight", b.feed_forward.w3.weight),
+                    (pre + "feed_forward.w2.weight", b.feed_forward.w2.weight)]
+        if m.model_type == "t2i":
+            out += [("cls_embedding.cap_proj.fc1.weight", m.cls_embedding.cap_proj.fc1.weight),
+                    ("cls_embedding.cap_proj.fc2.weight", m.cls_embedding.cap_proj.fc2.weight)]
+        else:
+            out += [("cls_embedding.embedding_table.weight", m.cls_embedding.embedding_table.weight)]
+        out += [("condition_mlp.cap_proj.fc1.weight", m.condition_mlp.cap_proj.fc1.weight),
+                ("condition_mlp.cap_proj.fc2.weight", m.condition_mlp.cap_proj.fc2.weight)]
+        for j in range(3):
+            out += [(f"condition_layers.{j}.fc1.weight", m.condition_layers[j].fc1.weight),
+                    (f"condition_layers.{j}.fc2.weight", m.condition_layers[j].fc2.weight)]
+        out += [("adapter_mlp.fc1.weight", m.adapter_mlp.fc1.weight), ("adapter_mlp.fc2.weight", m.adapter_mlp.fc2.weight)]
+        return out
+
+    def backward(self, module, loss_grad=None, want_feat_grad=True):
+        """Gradients of the last forward(targets=...) on this handle -> ({name: fp32 grad}, d_feat bf16 or None).
+        loss_grad: 0-dim / [1] fp32 CUDA tensor (d / d loss) or None = 1."""
+        from ._lib import CarTrainWeights
+        if getattr(self, "_last", None) is None:
+            raise RuntimeError("controlar_b200: backward() needs a preceding training forward with targets")
+        idx, cond, feat, drop, m8, tg, vf = self._last
+        if tg is None:
+            raise RuntimeError("controlar_b200: the last training forward had no targets / loss")
+        names = self.grad_params(module)
+        has_feat = feat is not None
+        skip_wo_feat = ("condition_mlp.", "condition_layers.", "adapter_mlp.")
+        G = {k: torch.empty_like(p, dtype=torch.float32) for k, p in names if has_feat or not k.startswith(skip_wo_feat)}
+        L = len(module.layers)
+        gw = CarTrainWeights()
+        keep = []
+
+        def P(key):
+            t = G.get(key)
+            return None if t is None else _ptr(t)
+        gw.w.tok_embeddings = P("tok_embeddings.weight"); gw.w.norm = P("norm.weight"); gw.w.output = P("output.weight")
+        for field, suffix in [("attention_norm", "attention_norm.weight"), ("wqkv", "attention.wqkv.weight"), ("wo", "attention.wo.weight"),
+                              ("ffn_norm", "ffn_norm.weight"), ("w1", "feed_forward.w1.weight"), ("w3", "feed_forward.w3.weight"),
+                              ("w2", "feed_forward.w2.weight")]:
+            arr = _ptr_array([G[f"layers.{i}.{suffix}"] for i in range(L)])
+            keep.append(arr)
+            setattr(gw.w, field, C.cast(arr, C.POINTER(C.c_void_p)))
+        if module.model_type == "t2i":
+            gw.w.cap_fc1 = P("cls_embedding.cap_proj.fc1.weight"); gw.w.cap_fc2 = P("cls_embedding.cap_proj.fc2.weight")
+        else:
+            gw.w.label_table = P("cls_embedding.embedding_table.weight")
+        gw.w.cond_fc1 = P("condition_mlp.cap_proj.fc1.weight"); gw.w.cond_fc2 = P("condition_mlp.cap_proj.fc2.weight")
+        for j in range(3):
+            gw.w.ctl_fc1[j] = P(f"condition_layers.{j}.fc1.weight"); gw.w.ctl_fc2[j] = P(f"condition_layers.{j}.fc2.weight")
+        gw.adapter_fc1 = P("adapter_mlp.fc1.weight"); gw.adapter_fc2 = P("adapter_mlp.fc2.weight")
+        dfeat = torch.empty_like(feat) if (has_feat and want_feat_grad) else None
+        lg = None
+        if loss_grad is not None:
+            lg = loss_grad.detach().to(device=idx.device, dtype=torch.float32).reshape(1).contiguous()
+        check(self.lib.car_train_backward(self.handle, C.byref(gw), None if dfeat is None else _ptr(dfeat), None if lg is None else _ptr(lg),
+                                          cur_stream()), "car_train_backward")
+        self._last = None
+        return G, dfeat
 
     def close(self):
         if self.handle:

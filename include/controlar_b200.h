@@ -220,7 +220,7 @@ int car_vq_destroy(CarVQ* m);
  * in train mode (autoregressive/models/gpt_t2i.py:420-431,451-484) as the train scripts run it — fp32 parameters under bf16
  * autocast (autoregressive/train/train_t2i_canny.py:166-167, train_c2i_canny.py:200-201).  Dropout layers at p = 0; the CFG
  * drop decision (gpt_t2i.py:83,116,148: torch.rand(B) < class_dropout_prob) is drawn by the caller and passed in.
- * Forward + loss only (no gradients yet).
+ * car_train_backward gives the gradients of every parameter on this path and of the control tokens.
  * ===================================================================================================== */
 typedef struct CarTrain CarTrain;
 typedef struct CarTrainWeights {
@@ -230,6 +230,8 @@ typedef struct CarTrainWeights {
     const void* cap_uncond;    /* cls_embedding.uncond_embedding [T, caption_dim] fp32 (t2i), else NULL */
     int32_t     adapter_dim;   /* 384 (DINOv2-small / ViT-S) | 768 (DINOv2-base) */
     int32_t     num_classes;   /* c2i: row of the dropped label in cls_embedding.embedding_table */
+    const void* cond_uncond;   /* condition_mlp.uncond_embedding [>= n_img, d] fp32 (a buffer: rows given to dropped samples,
+                                  gpt_t2i.py:107,120); NULL = zeros, which is what the released checkpoints hold */
 } CarTrainWeights;
 /* Workspaces are sized for max_batch sequences of cls_token_num + max_img_tokens - 1 rows.  Weights and rope_table
  * (fp32 [T + block_size, 32, 2], as for car_state_create) are borrowed until car_train_destroy. */
@@ -243,6 +245,15 @@ int car_train_create(const CarModelDesc* desc, const CarTrainWeights* weights, i
 int car_train_forward(CarTrain* t, int32_t B, int32_t n_img, const int32_t* idx, const void* cond, const void* feat,
                       const uint8_t* drop_ids, const uint8_t* mask, const int32_t* targets, const float* valid,
                       float* logits_out, float* loss_out, void* stream);
+/* Backward of the LAST car_train_forward(targets != NULL) on this handle (in the reference: autograd, train_c2i_canny.py:200-211
+ * `scaler.scale(loss).backward()`), recomputing each block from the fp32 stream saved at its input.  `grads` is a CarTrainWeights
+ * whose pointers address fp32 GRADIENT buffers of the parameters' shapes (every non-NULL one is overwritten with d loss / d param;
+ * cap_uncond / cond_uncond / the two int fields are ignored); d_feat: bf16 [B, n_img, adapter_dim] or NULL (the hand-over to the
+ * control encoder's own backward); loss_grad: device fp32 [1] multiplying every gradient (d / d loss, e.g. a GradScaler factor) or
+ * NULL = 1.  The tensors passed to that car_train_forward must still be alive.  Gradients are bf16-rounded where autograd under
+ * bf16 autocast rounds them (tests/test_zz_train_backward_gpu.py: <= 3e-2 rel-L2 per tensor against autograd over the oracle,
+ * itself pinned to gradients the reference produced).  Needs dim, ffn_dim, vocab_size multiples of 64. */
+int car_train_backward(CarTrain* t, const CarTrainWeights* grads, void* d_feat, const float* loss_grad, void* stream);
 int car_train_destroy(CarTrain* t);
 
 /* ---- antialiased bilinear resize in front of the online VQ encode of the multi-resolution training scripts:
