@@ -1104,14 +1104,12 @@ extern "C" int car_train_destroy(CarTrain* t) {
     return CAR_OK;
 }
 
-static int tr_attn_smem(int S, size_t floats_per_warp, const void* fn, bool* attr_set, size_t* bytes) {
+// dynamic shared memory of the plain attention kernels (TRA_WARPS warps x floats_per_warp); above 48 KB the opt-in attribute is set on
+// every call (cheap, and correct on every device of the process — no process-wide "already set" flag)
+static int tr_attn_smem(size_t floats_per_warp, const void* fn, size_t* bytes) {
     *bytes = (size_t)TRA_WARPS * floats_per_warp * 4;
-    (void)S;
     if (*bytes > 200 * 1024) CAR_FAIL(CAR_ERR_UNSUPPORTED, "sequence too long for the plain attention kernels");
-    if (*bytes > 48 * 1024 && !*attr_set) {
-        CAR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        *attr_set = true;
-    }
+    if (*bytes > 48 * 1024) CAR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return CAR_OK;
 }
 
@@ -1128,9 +1126,8 @@ static int tr_block_fwd(CarTrain* t, cudaStream_t st, int l, int B, int n_img, c
         CAR_LAUNCH(tr_add_rows_kernel, tr_grid((long long)RC * dim), 256, 0, st, t->h, (const bf16*)t->cadd, B, n_img, S, T - 1, dim);
     }
     if (for_bwd) CAR_CUDA(cudaMemcpyAsync(t->h0, t->h, (size_t)R * dim * 4, cudaMemcpyDeviceToDevice, st));
-    static bool attr_set = false;
     size_t att_smem = 0;
-    CAR_TRY(tr_attn_smem(S, (size_t)S, (const void*)tr_attention_kernel, &attr_set, &att_smem));
+    CAR_TRY(tr_attn_smem((size_t)S, (const void*)tr_attention_kernel, &att_smem));
     CAR_LAUNCH(tr_rmsnorm_kernel, R, 256, 0, st, (const float*)t->h, (const float*)t->attention_norm[l], t->x, dim, d.norm_eps, S, S, 0);
     CAR_TRY(dense_linear(st, t->x, dim, t->b_wqkv[l], R, 3 * dim, dim, ACT_NONE, nullptr, 0, t->qkv, 3 * dim));
     CAR_LAUNCH(rope_kv_write_kernel, 148 * 8, 256, 0, st, (const bf16*)t->qkv, t->rope, t->q, t->kc, t->vc, R, S, dim, H, S);
@@ -1264,10 +1261,9 @@ extern "C" int car_train_backward(CarTrain* t, const CarTrainWeights* g, void* d
     const int B = t->fB, n_img = t->fN, n = n_img - 1, S = T + n, R = B * S, RC = B * n_img, step3 = L / 3;
     const bool has_feat = t->f_feat != nullptr;
     const uint8_t* mask = t->f_mask;
-    static bool attr_q = false, attr_kv = false;
     size_t smem_q = 0, smem_kv = 0;
-    CAR_TRY(tr_attn_smem(S, (size_t)2 * S + 128, (const void*)tr_attn_bwd_q_kernel, &attr_q, &smem_q));
-    CAR_TRY(tr_attn_smem(S, (size_t)2 * S + 128, (const void*)tr_attn_bwd_kv_kernel, &attr_kv, &smem_kv));
+    CAR_TRY(tr_attn_smem((size_t)2 * S + 128, (const void*)tr_attn_bwd_q_kernel, &smem_q));
+    CAR_TRY(tr_attn_smem((size_t)2 * S + 128, (const void*)tr_attn_bwd_kv_kernel, &smem_kv));
     const unsigned att_grid = (unsigned)(((long long)B * H * S + TRA_WARPS - 1) / TRA_WARPS);
     t->fwd_ok = false;                                         // the recompute below overwrites the forward's buffers
     // ---- head: loss -> logits -> output projection -> final norm (gpt_t2i.py:469-481) ----
