@@ -4,8 +4,7 @@ size-independent properties of the conditional-decoding loop — the oracle need
   * run-to-run determinism (fixed reduction orders, counter-based sampler noise),
   * image independence: an image's token grid does not depend on the other images of the batch (rows of the M = 16 GEMMs,
     (b, h) pairs of the attention split and the per-image sampler never mix),
-  * every token is a valid code.
-NOT YET RUN ON A GPU (written after the round-1 GPU budget was spent; lives on the r2 prep branch until validated)."""
+  * every token is a valid code."""
 import pytest
 import torch
 

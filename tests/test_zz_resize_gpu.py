@@ -1,7 +1,7 @@
 """GPU: antialiased bilinear resize (reference train_t2i_depth_multiscale.py:44-56 calls
 F.interpolate(..., mode='bilinear', align_corners=False, antialias=True)) through the C ABI, against the CPU oracle
 (oracle/resize_oracle.py, itself pinned to torch on the CPU) and against torch's own CUDA kernel.  fp32; tolerance 1e-3 of the
-0..255 range (fp32 summation order and FMA contraction).  NOT YET RUN ON A GPU (lives on the r2-prep-f1 branch until validated)."""
+0..255 range (fp32 summation order and FMA contraction)."""
 import pytest
 import torch
 import torch.nn.functional as F

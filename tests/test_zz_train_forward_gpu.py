@@ -3,8 +3,7 @@ autocast) through the drop-in module — `model.train(); model(idx=..., cond_idx
 against the fixtures the reference itself produced in train mode (tests/golden/train_*.pt) and against oracle/train_oracle.py.
 Tolerance: the CUDA path rounds at the same places as autocast (bf16 GEMM operands and outputs, fp32 stream / norm / soft-max /
 loss); what differs is fp32 summation order inside GEMMs and attention => bf16-level noise on the logits: rel-L2 <= 1e-2 (the oracle
-itself sits at <= 1.7e-3 from the reference), loss within 2e-3 relative.
-NOT YET RUN ON A GPU (written after the round-1 GPU budget was spent; lives on the r2-prep-f1 branch until validated)."""
+itself sits at <= 1.7e-3 from the reference), loss within 2e-3 relative."""
 import pytest
 import torch
 
