@@ -52,6 +52,12 @@ class ModelArgs:                      # field-for-field the constructor surface 
 
 
 class Transformer(_t.Transformer):
+    # training branch (gpt.py:410-421,440-449): with cls_token_num = 1 and condition_token_num = 0 it is gpt_t2i's branch (control
+    # tokens added to every row, logits from row 0) except that ConditionEmbedder.token_drop hands dropped samples literal zeros
+    # (gpt.py:118-119) instead of the `uncond_embedding` buffer — pinned against the reference's gpt.py in train mode by
+    # tests/test_train_oracle_golden.py::test_legacy_gptpy_train_branch_is_the_same_arithmetic; forward / backward are inherited.
+    zero_uncond_on_drop = True
+
     def __init__(self, config: ModelArgs):
         if config.condition_token_num != 0:
             # the reference's own generate() cannot use condition_token_num > 0 (T = 1 + n at generate.py:154 while the

@@ -168,9 +168,11 @@ class ARTrainHandle:
             unc = m.cls_embedding.uncond_embedding.detach().to(torch.float32).contiguous()
             keep.append(unc)
             tw.cap_uncond = _ptr(unc)
-        cunc = m.condition_mlp.uncond_embedding.detach().to(torch.float32).contiguous()   # buffer, zeros unless a state dict says otherwise
-        keep.append(cunc)
-        tw.cond_uncond = _ptr(cunc)
+        if not getattr(m, "zero_uncond_on_drop", False):
+            cunc = m.condition_mlp.uncond_embedding.detach().to(torch.float32).contiguous()   # buffer, zeros unless a state dict says otherwise
+            keep.append(cunc)
+            tw.cond_uncond = _ptr(cunc)
+        # else: the legacy gpt.py class gives dropped samples literal zeros (gpt.py:118-119): NULL = zeros in the library
         d = CarModelDesc(dtype=_lib.CAR_F32, dim=cfg.dim, n_layer=cfg.n_layer, n_head=cfg.n_head,
                          ffn_dim=m.layers[0].feed_forward.w1.weight.shape[0], vocab_size=cfg.vocab_size,
                          cls_token_num=cfg.cls_token_num, block_size=cfg.block_size,
