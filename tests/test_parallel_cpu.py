@@ -3,6 +3,7 @@ finished token grids (controlar_b200/parallel.py).  The decode loop itself has n
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -89,7 +90,7 @@ def test_gloo_world2_gather_token_grids():
 # The library's backward reaches the parameters through a torch.autograd.Function, so DDP's gradient hooks fire as usual and the
 # bucketed all-reduce is torch's own: nothing to build, but it has to be shown to work.  The library calls are stubbed (no GPU
 # here): each rank's "backward" returns gradients equal to rank + 1, so every .grad must end at the mean 1.5 on both ranks.
-def _worker_ddp(rank: int, world: int, port: int, ret):
+def _worker_ddp(rank: int, world: int, port: int, ret, find_unused: bool):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -121,11 +122,13 @@ def _worker_ddp(rank: int, world: int, port: int, ret):
                                                   resid_dropout_p=0.0, ffn_dropout_p=0.0, class_dropout_prob=0.1)).train()
         # this library differentiates down to the control tokens: the control encoder (and the unused condition_embeddings table)
         # stay frozen, otherwise DDP waits for gradients that never come
-        trained = {id(p) for _, p in engine.ARTrainHandle.grad_params(m)}
-        for p in m.parameters():
-            p.requires_grad_(id(p) in trained)
+        if not find_unused:
+            trained = {id(p) for _, p in engine.ARTrainHandle.grad_params(m)}
+            for p in m.parameters():
+                p.requires_grad_(id(p) in trained)
         m.adapter.forward = lambda x: torch.zeros(x.shape[0], 16, 384)
-        ddp = DDP(m)
+        # find_unused: the reference's own call, DDP(model, find_unused_parameters=True) (train_c2i_canny.py:173), nothing frozen
+        ddp = DDP(m, find_unused_parameters=find_unused)
         with torch.enable_grad():
             for _ in range(2):                                   # two iterations: the reducer must be re-armed after the first
                 for p in m.parameters():
@@ -138,10 +141,11 @@ def _worker_ddp(rank: int, world: int, port: int, ret):
         dist.destroy_process_group()
 
 
-def test_ddp_over_the_library_backward():
+@pytest.mark.parametrize("find_unused", [False, True])
+def test_ddp_over_the_library_backward(find_unused):
     world = 2
     ret = mp.Manager().dict()
-    mp.spawn(_worker_ddp, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_worker_ddp, args=(world, _free_port(), ret, find_unused), nprocs=world, join=True)
     for rank in range(world):
         assert len(ret[rank]) > 20
         for k, (lo, hi) in ret[rank].items():
