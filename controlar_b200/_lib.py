@@ -136,6 +136,22 @@ def on_device(t):
     return torch.cuda.device(t.device)
 
 
+def _no_handle():
+    return None
+
+
+class NativeHandle:
+    """Base of the objects that own a library handle.  Handles are never copied: `copy.deepcopy` / pickling of the owning module
+    (e.g. `ema = deepcopy(model)` of the train scripts, train_c2i_canny.py:117, after the model has been used) yields None in the
+    copy, which rebuilds its own handle lazily on first use — instead of ctypes' "objects containing pointers cannot be pickled"."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_handle, ())
+
+
 def _ptr(t):
     """Device pointer of a contiguous CUDA tensor (None passes through)."""
     if t is None:

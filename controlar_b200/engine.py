@@ -29,7 +29,7 @@ def _on_own_device(fn):
     return wrapped
 
 
-class ARModelHandle:
+class ARModelHandle(_lib.NativeHandle):
     """CarModel: GEMM-ready copies of the transformer weights (re-packed when the module's weights change)."""
 
     def __init__(self, module):
@@ -147,7 +147,7 @@ class ARModelHandle:
             pass
 
 
-class ARTrainHandle:
+class ARTrainHandle(_lib.NativeHandle):
     """CarTrain: the teacher-forced training forward (reference gpt_t2i.py:420-431,451-484) on the module's fp32 parameters
     under bf16-autocast numerics.  Weights are borrowed (re-cast to bf16 inside every forward, like autocast does)."""
 
@@ -302,7 +302,7 @@ def self_like(module):
     return _ModuleView(module)
 
 
-class ARStateHandle:
+class ARStateHandle(_lib.NativeHandle):
     """CarState: KV caches (PyTorch-owned, reference layout), control tokens, scratch, the persistent decode kernel's packet
     buffers (and the CUDA graph of the per-kernel fallback chain)."""
 

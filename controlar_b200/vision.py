@@ -74,7 +74,7 @@ def _on_module_device(attr):
     return deco
 
 
-class DinoHandle:
+class DinoHandle(_lib.NativeHandle):
     def __init__(self, adapter, adapter_mlp=None):
         self.lib = _lib.lib()
         self.adapter, self.adapter_mlp = adapter, adapter_mlp
@@ -224,7 +224,7 @@ def vq_tensor_order(vq) -> List[torch.Tensor]:
     return out
 
 
-class VQHandle:
+class VQHandle(_lib.NativeHandle):
     def __init__(self, vq):
         self.lib = _lib.lib()
         self.vq = vq

@@ -88,3 +88,29 @@ def test_generate_and_forward_signatures_cover_the_reference():
     assert list(inspect.signature(ot.Transformer.forward).parameters) == rf
     rl = list(inspect.signature(_ref_module("autoregressive.models.gpt").Transformer.forward).parameters)
     assert list(inspect.signature(ol.Transformer.forward).parameters)[:len(rl)] == rl     # + control_strength (must stay 1)
+
+
+def test_modules_with_live_library_handles_can_be_deep_copied():
+    """`ema = deepcopy(model)` (train_c2i_canny.py:117) and `torch.save(model)` must work after the model has been used: library
+    handles are dropped from the copy (which rebuilds them lazily) instead of failing in ctypes' pickling."""
+    import copy
+    import ctypes as C
+    import pickle
+    from controlar_b200 import engine, vision
+    from controlar_b200.autoregressive.models.gpt_t2i import Transformer, ModelArgs
+
+    def fake(cls):
+        class F(cls):
+            def __init__(self):
+                self.handle = C.c_void_p(0)            # null: close() / __del__ have nothing to destroy
+
+            def close(self):
+                pass
+        return F()
+    m = Transformer(ModelArgs(dim=128, n_layer=3, n_head=2, vocab_size=64, cls_token_num=1, block_size=16, num_classes=10, model_type="c2i"))
+    m._car_model, m._car_state, m._car_train = fake(engine.ARModelHandle), fake(engine.ARStateHandle), fake(engine.ARTrainHandle)
+    object.__setattr__(m.adapter, "_car_dino", fake(vision.DinoHandle))
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._car_model is None and clone._car_state is None and clone._car_train is None and clone.adapter._car_dino is None
+        assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), clone.state_dict().values()))
+    assert m._car_model is not None                    # the original keeps its handles
